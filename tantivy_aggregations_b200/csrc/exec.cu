@@ -1,0 +1,484 @@
+// exec.cu — one `tagg_execute`: resolve columns, normalise docsets, size the bucket scopes, lay the
+// accumulator arena out in HBM, launch the kernels, read the fruit back.
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "exec.h"
+
+#define DENSE_MAX_BUCKETS (1ull << 24)
+#define HASH_MIN_CAP (1ull << 10)
+#define HASH_MAX_CAP (1ull << 30)
+
+ExecState::~ExecState() {
+    free_temps();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) ctx->release_stream(st);
+}
+void ExecState::free_temps() {
+    for (void* p : temps) cudaFreeAsync(p, st);
+    temps.clear();
+    if (arena) cudaFreeAsync(arena, st);
+    arena = nullptr;
+    if (d_plan) cudaFreeAsync(d_plan, st);
+    d_plan = nullptr;
+    for (int i = 0; i < 4; i++) {
+        if (pct_codes[i]) cudaFreeAsync(pct_codes[i], st);
+        if (pct_buckets[i]) cudaFreeAsync(pct_buckets[i], st);
+        if (pct_count[i]) cudaFreeAsync(pct_count[i], st);
+        pct_codes[i] = nullptr; pct_buckets[i] = nullptr; pct_count[i] = nullptr;
+    }
+}
+
+static inline double code_to_f64_h(uint64_t c) {
+    uint64_t bits = (c >> 63) ? (c ^ 0x8000000000000000ull) : ~c;
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+}
+// host twin of dev.cuh hist_ord (IEEE double arithmetic is identical on both sides)
+static bool hist_ord_h(uint64_t code, double start, double interval, uint64_t* ord) {
+    double k = code_to_f64_h(code);
+    if (k != k) return false;
+    volatile double n = k - start;
+    if (n < 0.0) return false;
+    volatile double q0 = n / interval;
+    double q = std::floor(q0);
+    if (!(q == q) || q <= 0.0) *ord = 0;
+    else if (q >= 18446744073709551616.0) *ord = ~0ull;
+    else *ord = (uint64_t)q;
+    return true;
+}
+static inline uint64_t pow2ceil(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <typename T>
+static int dev_alloc(ExecState& es, T** out, size_t bytes) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, es.st));
+    es.temps.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+
+// A docset argument -> what the kernels test (dev.cuh DevDocset).
+static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_docset& in, bool is_main,
+                            DevSegment& hs, int& next_col, DevDocset* out, uint64_t* n_cand) {
+    DevDocset d;
+    memset(&d, 0, sizeof(d));
+    size_t need = ((size_t)seg->max_doc + 7) / 8;
+    size_t words = ((size_t)seg->max_doc + 31) / 32 + 4;
+    switch (in.kind) {
+        case TAGG_DOCSET_ALL:
+            d.kind = DS_ALL;
+            if (n_cand) *n_cand = seg->max_doc;
+            break;
+        case TAGG_DOCSET_BITSET: {
+            if (need && (!in.data || in.n < need))
+                return tagg_fail(TAGG_ERR_BAD_ARG, "bitset docset needs %zu bytes for max_doc=%u, got %llu", need, seg->max_doc,
+                                 (unsigned long long)in.n);
+            uint32_t* w = nullptr;
+            int rc = dev_alloc(es, &w, words * 4);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(w + (words - 5), 0, 20, es.st));
+            if (need) CUDA_TRY(cudaMemcpyAsync(w, in.data, need, cudaMemcpyHostToDevice, es.st));
+            d.kind = DS_BITSET;
+            d.words = w;
+            if (n_cand) *n_cand = seg->max_doc;
+            es.alg_bytes += need;
+            break;
+        }
+        case TAGG_DOCSET_SORTED_IDS: {
+            if (in.n && !in.data) return tagg_fail(TAGG_ERR_BAD_ARG, "null doc-id list");
+            uint32_t* ids = nullptr;
+            int rc = dev_alloc(es, &ids, in.n * 4);
+            if (rc) return rc;
+            if (in.n) CUDA_TRY(cudaMemcpyAsync(ids, in.data, in.n * 4, cudaMemcpyHostToDevice, es.st));
+            es.alg_bytes += in.n * 4;
+            if (is_main) {
+                d.kind = DS_IDS;
+                d.ids = ids;
+                d.n = in.n;
+                if (n_cand) *n_cand = in.n;
+            } else {  // filters are tested per doc: scatter the ids into a bitset (K6)
+                uint32_t* w = nullptr;
+                rc = dev_alloc(es, &w, words * 4);
+                if (rc) return rc;
+                CUDA_TRY(cudaMemsetAsync(w, 0, words * 4, es.st));
+                CUDA_TRY(launch_ids_to_bitset(ids, in.n, w, es.st));
+                if (in.n) { es.ctx->launches++; es.n_launches++; }
+                d.kind = DS_BITSET;
+                d.words = w;
+            }
+            break;
+        }
+        case TAGG_DOCSET_COLUMN_RANGE: {
+            auto it = seg->cols.find(in.field_id);
+            if (it == seg->cols.end())
+                return tagg_fail(TAGG_ERR_NO_SUCH_COLUMN, "docset field %u is not a single-valued fast field of the segment", in.field_id);
+            int slot = -1;
+            for (int c = 0; c < next_col; c++)
+                if (hs.cols[c].words == (const uint64_t*)it->second.dptr && hs.cols[c].num_bits == it->second.num_bits &&
+                    hs.cols[c].min_value == it->second.min_value && it->second.dptr)
+                    slot = c;
+            if (slot < 0) {
+                if (next_col >= TAGG_MAX_COLS) return tagg_fail(TAGG_ERR_BAD_PLAN, "too many device columns");
+                slot = next_col++;
+                hs.cols[slot] = it->second.dev();
+                es.alg_bytes += it->second.payload_bytes + 16;
+            }
+            d.kind = DS_RANGE;
+            d.col = slot;
+            d.lo = in.lo;
+            d.hi = in.hi;
+            if (n_cand) *n_cand = seg->max_doc;
+            break;
+        }
+        default: return tagg_fail(TAGG_ERR_BAD_ARG, "unknown docset kind %d", in.kind);
+    }
+    *out = d;
+    return 0;
+}
+
+static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uint32_t n_inputs) {
+    const PlanMeta& m = *es.meta;
+    es.hsegs.resize(n_inputs);
+    es.n_cand.assign(n_inputs, 0);
+    for (uint32_t i = 0; i < n_inputs; i++) {
+        const tagg_segment* seg = inputs[i].segment;
+        if (!seg) return tagg_fail(TAGG_ERR_BAD_ARG, "input %u: null segment", i);
+        if (seg->ctx != es.ctx) return tagg_fail(TAGG_ERR_BAD_ARG, "input %u: segment belongs to another context", i);
+        if (inputs[i].n_filters < m.n_filters)
+            return tagg_fail(TAGG_ERR_BAD_ARG, "input %u: plan has %u filter_agg nodes but %u filter docsets were given", i,
+                             m.n_filters, inputs[i].n_filters);
+        es.segs.push_back(seg);
+        DevSegment& hs = es.hsegs[i];
+        memset(&hs, 0, sizeof(hs));
+        hs.max_doc = seg->max_doc;
+        hs.has_deletes = seg->has_deletes ? 1 : 0;
+        hs.deleted = seg->d_deleted;
+        if (seg->has_deletes) es.alg_bytes += ((size_t)seg->max_doc + 7) / 8;
+        int at = 0;
+        for (auto& r : m.colrefs) {
+            if (r.multi) {
+                auto it = seg->mcols.find(r.field_id);
+                if (it == seg->mcols.end())
+                    return tagg_fail(TAGG_ERR_NO_SUCH_COLUMN, "field %u is not a multi-valued fast field of segment %u", r.field_id, i);
+                hs.cols[at++] = it->second.first.dev();
+                hs.cols[at++] = it->second.second.dev();
+                es.alg_bytes += it->second.first.payload_bytes + it->second.second.payload_bytes + 32;
+            } else {
+                auto it = seg->cols.find(r.field_id);
+                if (it == seg->cols.end())
+                    return tagg_fail(TAGG_ERR_NO_SUCH_COLUMN, "field %u is not a single-valued fast field of segment %u", r.field_id, i);
+                hs.cols[at++] = it->second.dev();
+                es.alg_bytes += it->second.payload_bytes + 16;
+            }
+        }
+        int next_col = at;
+        int rc = normalise_docset(es, seg, inputs[i].docset, true, hs, next_col, &hs.main, &es.n_cand[i]);
+        if (rc) return rc;
+        for (uint32_t f = 0; f < m.n_filters; f++) {
+            rc = normalise_docset(es, seg, inputs[i].filters[f], false, hs, next_col, &hs.filters[f], nullptr);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// Key domain of every bucket scope over the segments of this call (absolute codes / ordinals, so
+// one table serves all segments — and, after comm_agree_domains, all ranks).
+// dom[3*s+0] = smallest key (~0: none seen), [1] = ~(largest key), [2] = 1 if a dense table is possible.
+static int scope_domains_local(ExecState& es, std::vector<uint64_t>& dom, std::vector<uint64_t>& bounds) {
+    const PlanMeta& m = *es.meta;
+    size_t ns = m.scope_node.size();
+    dom.assign(ns * 3, 0);
+    bounds.assign(ns, 0);
+    for (size_t s = 1; s < ns; s++) {
+        int node = m.scope_node[s];
+        const tagg_node& nd = m.nodes[node];
+        bool have = false;
+        uint64_t lo = 0, hi = 0, bound = 0;
+        for (size_t i = 0; i < es.segs.size(); i++) {
+            const HostColumn* c = nd.multi ? &es.segs[i]->mcols.at(nd.field_id).second : &es.segs[i]->cols.at(nd.field_id);
+            bound += nd.multi ? c->n_values : es.n_cand[i];
+            if (c->n_values == 0) continue;
+            uint64_t a = c->min_value, b = c->min_value + c->amplitude;
+            lo = have ? std::min(lo, a) : a;
+            hi = have ? std::max(hi, b) : b;
+            have = true;
+        }
+        bounds[s] = bound;
+        uint64_t dense_ok = 1, dmin = ~0ull, dmax = 0;
+        if (have) {
+            if (nd.op == TAGG_OP_TERMS) {
+                dmin = lo;
+                dmax = hi;
+            } else {
+                double start = nd.f0, interval = nd.f1;
+                if (!(start == start) || !(interval > 0.0) || std::isinf(interval) || std::isinf(start)) {
+                    dense_ok = 0;
+                } else {
+                    uint64_t olo = 0, ohi = 0;
+                    bool vlo = hist_ord_h(lo, start, interval, &olo);
+                    bool vhi = hist_ord_h(hi, start, interval, &ohi);
+                    if (!vlo) olo = 0;  // the smallest valid k is >= start, whose ordinal is >= 0
+                    if (!vhi) {
+                        double khi = code_to_f64_h(hi);
+                        ohi = (khi != khi && (hi >> 63)) ? ~0ull : olo;  // +NaN codes lie above +inf; below start: nothing valid
+                    }
+                    if (ohi < olo) ohi = olo;
+                    dmin = olo;
+                    dmax = ohi;
+                }
+            }
+        }
+        dom[3 * s] = dmin;
+        dom[3 * s + 1] = ~dmax;
+        dom[3 * s + 2] = dense_ok;
+    }
+    return 0;
+}
+
+static int finalize_scopes(ExecState& es, const std::vector<uint64_t>& dom, const std::vector<uint64_t>& bounds) {
+    const PlanMeta& m = *es.meta;
+    size_t ns = m.scope_node.size();
+    es.scopes.assign(ns, ScopeLayout());
+    for (size_t s = 1; s < ns; s++) {
+        ScopeLayout& L = es.scopes[s];
+        const ScopeLayout& PL = es.scopes[m.scope_parent[s]];
+        uint64_t dmin = dom[3 * s], dmax = ~dom[3 * s + 1];
+        bool dense_ok = dom[3 * s + 2] != 0;
+        if (dmin == ~0ull && dmax == 0) { dmin = 0; dmax = 0; }  // no values anywhere
+        uint64_t dsize = dmax - dmin + 1;                         // 0 on full-range wrap
+        if (dsize == 0) dense_ok = false;
+        if (PL.mode != SCOPE_DENSE) dense_ok = false;
+        if (dense_ok) {
+            unsigned __int128 cap = (unsigned __int128)PL.capacity * dsize;
+            if (cap > DENSE_MAX_BUCKETS) dense_ok = false;
+        }
+        if (dense_ok) {
+            L.mode = SCOPE_DENSE;
+            L.dom_min = dmin;
+            L.dom_size = dsize;
+            L.capacity = PL.capacity * dsize;
+        } else {
+            L.mode = SCOPE_HASH;
+            uint64_t want = std::max<uint64_t>(bounds[s], 1) * 2;
+            uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(pow2ceil(want), HASH_MIN_CAP), 1ull << 22);
+            cap <<= es.hash_shift;
+            if (cap > HASH_MAX_CAP) return tagg_fail(TAGG_ERR_OOM, "bucket table would exceed %llu slots", (unsigned long long)HASH_MAX_CAP);
+            L.capacity = cap;
+        }
+    }
+    return 0;
+}
+
+static int layout_arena(ExecState& es) {
+    const PlanMeta& m = *es.meta;
+    size_t off = 0;
+    es.off_overflow = off;
+    off += 16;
+    for (size_t s = 0; s < es.scopes.size(); s++) {
+        ScopeLayout& L = es.scopes[s];
+        if (L.mode == SCOPE_DENSE) {
+            L.off_present = off;
+            off = align16(off + L.capacity);
+        } else {
+            L.off_keys = off; off = align16(off + L.capacity * 8);
+            L.off_parents = off; off = align16(off + L.capacity * 4);
+            L.off_state = off; off = align16(off + L.capacity * 4);
+            L.off_used = off; off += 16;
+        }
+    }
+    es.slots.assign(m.slot_node.size(), SlotLayout());
+    for (size_t k = 0; k < m.slot_node.size(); k++) {
+        SlotLayout& S = es.slots[k];
+        S.capacity = es.scopes[m.scope_of[m.slot_node[k]]].capacity;
+        S.off_acc = off; off = align16(off + S.capacity * 8);
+        S.off_seen = off; off = align16(off + S.capacity);
+    }
+    es.arena_bytes = off;
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, es.arena_bytes, es.st));
+    es.arena = (uint8_t*)p;
+    CUDA_TRY(cudaMemsetAsync(es.arena, 0, es.arena_bytes, es.st));
+    return 0;
+}
+
+static int build_dev_plan(ExecState& es) {
+    const PlanMeta& m = *es.meta;
+    DevPlan& P = es.hplan;
+    memset(&P, 0, sizeof(P));
+    P.n_nodes = (uint32_t)m.nodes.size();
+    P.n_scopes = (uint32_t)es.scopes.size();
+    P.n_slots = (uint32_t)es.slots.size();
+    for (int i = 0; i < TAGG_MAX_NODES; i++) P.slot_root_index[i] = -1;
+    for (uint32_t i = 0; i < P.n_nodes; i++) {
+        const tagg_node& nd = m.nodes[i];
+        DevNode& d = P.nodes[i];
+        d.op = nd.op; d.kind = nd.kind; d.multi = nd.multi; d.pred = nd.pred;
+        d.col = (uint16_t)(m.col_slot[i] < 0 ? 0 : m.col_slot[i]);
+        d.end = m.end[i];
+        d.scope = (uint16_t)m.scope_of[i];
+        d.own_scope = (uint16_t)(m.own_scope[i] < 0 ? 0 : m.own_scope[i]);
+        d.slot = (uint16_t)(m.slot_of[i] < 0 ? 0 : m.slot_of[i]);
+        d.aux = (uint16_t)(nd.op == TAGG_OP_PERCENTILES ? m.pct_of[i] : nd.aux);
+        d.lut = (nd.op == TAGG_OP_POST_FILTER && nd.pred == TAGG_PRED_LUT) ? es.plan->d_blobs[nd.aux] : nullptr;
+        d.f0 = nd.f0; d.f1 = nd.f1; d.u0 = nd.u0; d.u1 = nd.u1;
+    }
+    for (size_t s = 0; s < es.scopes.size(); s++) {
+        const ScopeLayout& L = es.scopes[s];
+        DevScope& d = P.scopes[s];
+        d.mode = L.mode;
+        d.parent = m.scope_parent[s];
+        d.capacity = L.capacity;
+        d.dom_min = L.dom_min;
+        d.dom_size = L.dom_size;
+        if (L.mode == SCOPE_DENSE) {
+            d.present = es.arena + L.off_present;
+        } else {
+            d.keys = (uint64_t*)(es.arena + L.off_keys);
+            d.parents = (uint32_t*)(es.arena + L.off_parents);
+            d.state = (uint32_t*)(es.arena + L.off_state);
+            d.used = (unsigned long long*)(es.arena + L.off_used);
+        }
+    }
+    uint32_t nroot = 0;
+    for (size_t k = 0; k < es.slots.size(); k++) {
+        P.slots[k].acc = (uint64_t*)(es.arena + es.slots[k].off_acc);
+        P.slots[k].seen = es.arena + es.slots[k].off_seen;
+        int node = m.slot_node[k];
+        if (m.scope_of[node] == 0 && nroot < TAGG_MAX_ROOT_SLOTS) {
+            P.slot_root_index[k] = (int16_t)nroot;
+            P.root_slot_nodes[nroot++] = (uint16_t)node;
+        }
+    }
+    P.n_root_slots = nroot;
+    P.overflow = (uint32_t*)(es.arena + es.off_overflow);
+    // percentile materialisation: capacity = every value that could be inserted
+    for (size_t k = 0; k < m.pct_node.size(); k++) {
+        const tagg_node& nd = m.nodes[m.pct_node[k]];
+        uint64_t cap = 0;
+        for (size_t i = 0; i < es.segs.size(); i++)
+            cap += nd.multi ? es.segs[i]->mcols.at(nd.field_id).second.n_values : es.n_cand[i];
+        es.pct_cap[k] = cap;
+        void* p = nullptr;
+        CUDA_TRY(cudaMallocAsync(&p, cap * 8 + 16, es.st)); es.pct_codes[k] = (uint64_t*)p;
+        CUDA_TRY(cudaMallocAsync(&p, cap * 4 + 16, es.st)); es.pct_buckets[k] = (uint32_t*)p;
+        CUDA_TRY(cudaMallocAsync(&p, 16, es.st)); es.pct_count[k] = (unsigned long long*)p;
+        CUDA_TRY(cudaMemsetAsync(es.pct_count[k], 0, 16, es.st));
+        P.pct_codes[k] = es.pct_codes[k];
+        P.pct_buckets[k] = es.pct_buckets[k];
+        P.pct_count[k] = es.pct_count[k];
+        P.pct_cap[k] = cap;
+    }
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, sizeof(DevPlan), es.st));
+    es.d_plan = (DevPlan*)p;
+    CUDA_TRY(cudaMemcpyAsync(es.d_plan, &P, sizeof(DevPlan), cudaMemcpyHostToDevice, es.st));
+    return 0;
+}
+
+int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, bool collective,
+             tagg_result** out) {
+    if (!plan || !out || (n_inputs && !inputs)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_execute: null argument");
+    tagg_ctx* ctx = plan->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "tagg_execute_collective needs tagg_comm_init first");
+
+    ExecState es;
+    es.ctx = ctx;
+    es.plan = plan;
+    es.meta = plan->meta.get();
+    es.collective = collective;
+    es.st = ctx->acquire_stream();
+    CUDA_TRY(cudaEventCreate(&es.ev0));
+    CUDA_TRY(cudaEventCreate(&es.ev1));
+
+    int rc = resolve_segments(es, inputs, n_inputs);
+    if (rc) return rc;
+    if (n_inputs) {
+        rc = dev_alloc(es, &es.d_segs, sizeof(DevSegment) * n_inputs);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.hsegs.data(), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
+    }
+
+    float ms_total = 0;
+    for (int attempt = 0;; attempt++) {
+        std::vector<uint64_t> dom, bounds;
+        rc = scope_domains_local(es, dom, bounds);
+        if (rc) return rc;
+        if (collective) {
+            rc = comm_agree_domains(es, dom);
+            if (rc) return rc;
+        }
+        rc = finalize_scopes(es, dom, bounds);
+        if (rc) return rc;
+        rc = layout_arena(es);
+        if (rc) return rc;
+        rc = build_dev_plan(es);
+        if (rc) return rc;
+
+        CUDA_TRY(cudaEventRecord(es.ev0, es.st));
+        int handled = 0;
+        if (ctx->path != 1) {
+            handled = stream_try(es);
+            if (handled < 0) return -handled;
+        }
+        if (!handled) {
+            if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
+            es.path_used = 1;
+            for (uint32_t i = 0; i < n_inputs; i++) {
+                CUDA_TRY(launch_generic(es.d_plan, es.d_segs + i, es.n_cand[i], ctx->sm_count, es.st));
+                if (es.n_cand[i]) { ctx->launches++; es.n_launches++; }
+            }
+        }
+        CUDA_TRY(cudaEventRecord(es.ev1, es.st));
+        uint32_t overflow = 0;
+        CUDA_TRY(cudaMemcpyAsync(&overflow, es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
+        CUDA_TRY(cudaStreamSynchronize(es.st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, es.ev0, es.ev1);
+        ms_total += ms;
+        if (!overflow) break;
+        if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
+        if (attempt >= 6) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
+        // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
+        es.hash_shift += 2;
+        cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
+        cudaFreeAsync(es.d_plan, es.st); es.d_plan = nullptr;
+        for (int k = 0; k < 4; k++) {
+            if (es.pct_codes[k]) cudaFreeAsync(es.pct_codes[k], es.st);
+            if (es.pct_buckets[k]) cudaFreeAsync(es.pct_buckets[k], es.st);
+            if (es.pct_count[k]) cudaFreeAsync(es.pct_count[k], es.st);
+            es.pct_codes[k] = nullptr; es.pct_buckets[k] = nullptr; es.pct_count[k] = nullptr;
+        }
+    }
+
+    if (collective) {
+        rc = comm_merge_arena(es);
+        if (rc) return rc;
+    }
+
+    auto* res = new tagg_result();
+    res->meta = plan->meta;
+    rc = read_result(es, res);
+    if (rc) {
+        delete res;
+        return rc;
+    }
+    res->kernel_ms = ms_total;
+    res->alg_bytes = es.alg_bytes;
+    res->n_launches = es.n_launches;
+    res->path_used = es.path_used;
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    *out = res;
+    return 0;
+}

@@ -1,0 +1,61 @@
+// exec.h — state of one tagg_execute call, shared by exec.cu / stream.cu / result.cu / comm.cu.
+#pragma once
+#include "host.h"
+
+struct ScopeLayout {
+    int mode = SCOPE_DENSE;
+    uint64_t capacity = 1;
+    uint64_t dom_min = 0, dom_size = 1;
+    size_t off_present = 0, off_keys = 0, off_parents = 0, off_state = 0, off_used = 0;
+};
+struct SlotLayout {
+    size_t off_acc = 0, off_seen = 0;
+    uint64_t capacity = 1;
+};
+
+struct ExecState {
+    tagg_ctx* ctx = nullptr;
+    const tagg_plan* plan = nullptr;
+    const PlanMeta* meta = nullptr;
+    cudaStream_t st = nullptr;
+    bool collective = false;
+
+    std::vector<const tagg_segment*> segs;
+    std::vector<DevSegment> hsegs;
+    DevSegment* d_segs = nullptr;
+    std::vector<uint64_t> n_cand;    // candidates per segment (ids count or max_doc)
+    std::vector<void*> temps;        // device allocations to release at the end
+
+    std::vector<ScopeLayout> scopes;
+    std::vector<SlotLayout> slots;
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t off_overflow = 0;
+    DevPlan hplan;
+    DevPlan* d_plan = nullptr;
+
+    // percentile materialisation buffers (generic path)
+    uint64_t* pct_codes[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* pct_buckets[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* pct_count[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t pct_cap[4] = {0, 0, 0, 0};
+
+    uint64_t alg_bytes = 0;
+    uint32_t n_launches = 0;
+    uint32_t path_used = 0;
+    int hash_shift = 0;  // growth applied to hash scopes after an overflow
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~ExecState();
+    void free_temps();
+};
+
+int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, bool collective,
+             tagg_result** out);
+// result.cu: device accumulators -> compact host result
+int read_result(ExecState& es, tagg_result* res);
+// comm.cu: merge the accumulators of all ranks in place (dense scopes), before read_result
+int comm_agree_domains(ExecState& es, std::vector<uint64_t>& dom);
+int comm_merge_arena(ExecState& es);
+// stream.cu: returns 1 if a streaming fast shape handled the plan, 0 if not applicable, <0 = -status
+int stream_try(ExecState& es);

@@ -1,0 +1,129 @@
+// host.h — host-side internals of libtagg.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tagg.h"
+#include "../../include/tagg_synth.h"
+#include "dev.cuh"
+
+// ---- error plumbing ---------------------------------------------------------------------------
+int tagg_fail(int status, const char* fmt, ...);
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return tagg_fail(_e == cudaErrorMemoryAllocation ? TAGG_ERR_OOM : TAGG_ERR_CUDA,   \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- handles ------------------------------------------------------------------------------------
+struct tagg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int path = 0;
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;
+    std::vector<cudaStream_t> stream_pool;
+    // NCCL (comm.cu), loaded lazily with dlopen so that single-GPU use has no NCCL dependency
+    void* nccl = nullptr;  // opaque NcclState*
+    int rank = 0, n_ranks = 1;
+
+    cudaStream_t acquire_stream();
+    void release_stream(cudaStream_t s);
+};
+
+struct HostColumn {
+    void* dptr = nullptr;       // allocation (payload, zero padded)
+    size_t alloc_bytes = 0;
+    size_t payload_bytes = 0;   // ceil(n_values * num_bits / 8)
+    uint64_t min_value = 0, amplitude = 0, n_values = 0;
+    uint32_t num_bits = 0;
+    int kind = 0;
+    DevColumn dev() const {
+        DevColumn d;
+        d.words = (const uint64_t*)dptr;
+        d.min_value = min_value;
+        d.mask = num_bits == 64 ? ~0ull : ((1ull << num_bits) - 1ull);
+        d.n_values = n_values;
+        d.num_bits = num_bits;
+        d.kind = (uint32_t)kind;
+        return d;
+    }
+};
+
+struct tagg_segment {
+    tagg_ctx* ctx = nullptr;
+    uint32_t max_doc = 0;
+    std::unordered_map<uint32_t, HostColumn> cols;                          // single-valued
+    std::unordered_map<uint32_t, std::pair<HostColumn, HostColumn>> mcols;  // (idx, vals)
+    uint32_t* d_deleted = nullptr;
+    bool has_deletes = false;
+    uint64_t n_deleted = 0;
+};
+
+// Derived, immutable description of a plan (shared with its results).
+struct PlanMeta {
+    std::vector<tagg_node> nodes;
+    std::vector<uint16_t> end;        // one past the sub-tree
+    std::vector<int> parent_node;     // -1 for the root node
+    std::vector<int> scope_of;        // enclosing scope of each node
+    std::vector<int> own_scope;       // TERMS / HISTOGRAM: scope keyed by the node, else -1
+    std::vector<int> slot_of;         // leaf metric: slot id, else -1
+    std::vector<int> pct_of;          // PERCENTILES: percentile slot id, else -1
+    std::vector<int> scope_node;      // scope -> node index (-1 for root)
+    std::vector<int> scope_parent;    // scope -> parent scope (-1 for root)
+    std::vector<int> slot_node;       // slot -> node
+    std::vector<int> pct_node;
+    struct ColRef { uint32_t field_id; int multi; };
+    std::vector<ColRef> colrefs;      // device column slots: single -> 1 slot, multi -> 2 (idx, vals)
+    std::vector<int> col_slot;        // node -> first device column slot, -1 if none
+    uint32_t n_filters = 0;
+    std::vector<std::vector<uint8_t>> blobs;
+};
+
+struct tagg_plan {
+    tagg_ctx* ctx = nullptr;
+    std::shared_ptr<PlanMeta> meta;
+    std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
+};
+
+struct PctSummary {
+    uint64_t n_total = 0;
+    std::vector<uint64_t> ranks, value_bits;       // exact (rank, value) pairs, ascending
+    std::vector<uint64_t> rank_lo, rank_hi;        // after a merge ranks are intervals; empty = exact
+};
+
+struct tagg_result {
+    std::shared_ptr<PlanMeta> meta;
+    struct Scope { std::vector<uint64_t> keys; std::vector<uint32_t> parents; };
+    struct Slot { std::vector<uint64_t> values; std::vector<uint8_t> seen; };
+    std::vector<Scope> scopes;   // by scope id
+    std::vector<Slot> slots;     // by slot id
+    std::vector<std::unordered_map<uint64_t, PctSummary>> pcts;  // by pct slot: bucket -> summary
+    double kernel_ms = 0;
+    uint64_t alg_bytes = 0;
+    uint32_t n_launches = 0;
+    uint32_t path_used = 0;
+};
+
+// ---- kernels' launchers (generic.cu, stream.cu, columns.cu) ------------------------------------------
+cudaError_t launch_generic(const DevPlan* dplan, const DevSegment* dseg, uint64_t n_cand, int sm_count,
+                           cudaStream_t stream);
+
+// columns.cu
+int column_from_bytes(tagg_ctx* ctx, int kind, const uint8_t* bytes, size_t len, uint64_t n_values, HostColumn* out);
+int column_from_device_codes(tagg_ctx* ctx, int kind, const uint64_t* d_codes, uint64_t n, HostColumn* out,
+                             cudaStream_t stream);
+void column_free(HostColumn* c);
+cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* words, cudaStream_t stream);
+
+// result.cu
+int result_merge(tagg_result* dst, const tagg_result* src);

@@ -1,0 +1,390 @@
+// result.cu — device accumulators -> compact host fruit, the result readers of the ABI, and
+// `PreparedAgg::merge` (count.rs:39-41, sum.rs:59-70, minmax.rs:59-72, terms.rs:85-92,
+// histogram.rs:90-97, percentile.rs:58-62) on compact results.
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <unordered_map>
+
+#include "exec.h"
+
+#define FULL_COPY_MAX (1ull << 20)  // scopes up to this capacity are copied whole and compacted on the host
+
+template <typename T>
+__global__ void k_gather(const T* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ dst) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = src[idx[i]];
+}
+__global__ void k_gather_ranks(const uint64_t* __restrict__ sorted, const uint64_t* __restrict__ ranks, uint64_t n,
+                               uint64_t* __restrict__ dst) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = sorted[ranks[i] - 1];
+}
+
+static inline uint64_t code_to_bits_h(int kind, uint64_t c) {
+    if (kind == TAGG_U64) return c;
+    if (kind == TAGG_F64) return (c >> 63) ? (c ^ 0x8000000000000000ull) : ~c;
+    return c ^ 0x8000000000000000ull;
+}
+
+// values of `raw` indices out of a device array of `capacity` elements
+template <typename T>
+static int fetch(ExecState& es, const T* d_src, uint64_t capacity, const std::vector<uint32_t>& raw, const uint32_t* d_raw,
+                 std::vector<T>& out) {
+    out.resize(raw.size());
+    if (raw.empty()) return 0;
+    if (capacity <= FULL_COPY_MAX) {
+        std::vector<T> full(capacity);
+        CUDA_TRY(cudaMemcpyAsync(full.data(), d_src, capacity * sizeof(T), cudaMemcpyDeviceToHost, es.st));
+        CUDA_TRY(cudaStreamSynchronize(es.st));
+        for (size_t i = 0; i < raw.size(); i++) out[i] = full[raw[i]];
+        return 0;
+    }
+    T* d_dst = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_dst, raw.size() * sizeof(T), es.st));
+    unsigned blocks = (unsigned)std::min<uint64_t>((raw.size() + 255) / 256, 4096);
+    k_gather<T><<<blocks, 256, 0, es.st>>>(d_src, d_raw, raw.size(), d_dst);
+    es.ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out.data(), d_dst, raw.size() * sizeof(T), cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    cudaFreeAsync(d_dst, es.st);
+    return 0;
+}
+
+// Ranks kept from an exactly sorted multiset of n values: every rank up to 4096, then a geometric
+// schedule with ratio 1 + eps/4 (eps = 0.01, percentile.rs:174) so that any target rank k has a
+// stored rank within eps*k/8 — always inside CKMS's own +-eps*k band.
+static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks) {
+    ranks.clear();
+    uint64_t dense = std::min<uint64_t>(n, 4096);
+    for (uint64_t r = 1; r <= dense; r++) ranks.push_back(r);
+    uint64_t r = dense;
+    while (r < n) {
+        uint64_t nx = r + std::max<uint64_t>(1, (uint64_t)((double)r * 0.0025));
+        if (nx > n) nx = n;
+        ranks.push_back(nx);
+        r = nx;
+    }
+}
+
+static int read_percentiles(ExecState& es, tagg_result* res) {
+    const PlanMeta& m = *es.meta;
+    res->pcts.resize(m.pct_node.size());
+    for (size_t k = 0; k < m.pct_node.size(); k++) {
+        PctSummary sum;
+        unsigned long long n = 0;
+        CUDA_TRY(cudaMemcpyAsync(&n, es.pct_count[k], 8, cudaMemcpyDeviceToHost, es.st));
+        CUDA_TRY(cudaStreamSynchronize(es.st));
+        if (n > es.pct_cap[k]) n = es.pct_cap[k];
+        sum.n_total = n;
+        if (n) {
+            uint64_t* d_alt = nullptr;
+            void* d_tmp = nullptr;
+            CUDA_TRY(cudaMallocAsync((void**)&d_alt, n * 8, es.st));
+            cub::DoubleBuffer<uint64_t> keys(es.pct_codes[k], d_alt);
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (int)n, 0, 64, es.st);
+            CUDA_TRY(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, es.st));
+            CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, keys, (int)n, 0, 64, es.st));
+            rank_schedule(n, sum.ranks);
+            uint64_t *d_ranks = nullptr, *d_out = nullptr;
+            size_t nr = sum.ranks.size();
+            CUDA_TRY(cudaMallocAsync((void**)&d_ranks, nr * 8, es.st));
+            CUDA_TRY(cudaMallocAsync((void**)&d_out, nr * 8, es.st));
+            CUDA_TRY(cudaMemcpyAsync(d_ranks, sum.ranks.data(), nr * 8, cudaMemcpyHostToDevice, es.st));
+            k_gather_ranks<<<(unsigned)std::min<uint64_t>((nr + 255) / 256, 1024), 256, 0, es.st>>>(keys.Current(), d_ranks, nr, d_out);
+            es.ctx->launches++;
+            CUDA_TRY(cudaGetLastError());
+            sum.value_bits.resize(nr);
+            CUDA_TRY(cudaMemcpyAsync(sum.value_bits.data(), d_out, nr * 8, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaStreamSynchronize(es.st));
+            for (auto& v : sum.value_bits) v = code_to_bits_h(TAGG_F64, v);
+            cudaFreeAsync(d_alt, es.st); cudaFreeAsync(d_tmp, es.st); cudaFreeAsync(d_ranks, es.st); cudaFreeAsync(d_out, es.st);
+        }
+        res->pcts[k][0] = std::move(sum);
+    }
+    return 0;
+}
+
+int read_result(ExecState& es, tagg_result* res) {
+    const PlanMeta& m = *es.meta;
+    size_t ns = es.scopes.size();
+    res->scopes.assign(ns, tagg_result::Scope());
+    res->slots.assign(es.slots.size(), tagg_result::Slot());
+    std::vector<std::vector<uint32_t>> raw(ns);   // ascending raw bucket indices that exist
+    std::vector<uint32_t*> d_raw(ns, nullptr);
+
+    raw[0] = {0};
+    res->scopes[0].keys = {0};
+    res->scopes[0].parents = {0};
+    for (size_t s = 1; s < ns; s++) {
+        const ScopeLayout& L = es.scopes[s];
+        const tagg_node& nd = m.nodes[m.scope_node[s]];
+        int ps = m.scope_parent[s];
+        std::vector<uint64_t> keys;
+        std::vector<uint32_t> praw;
+        if (L.mode == SCOPE_DENSE) {
+            std::vector<uint8_t> present(L.capacity);
+            CUDA_TRY(cudaMemcpyAsync(present.data(), es.arena + L.off_present, L.capacity, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaStreamSynchronize(es.st));
+            for (uint64_t i = 0; i < L.capacity; i++)
+                if (present[i]) raw[s].push_back((uint32_t)i);
+            keys.resize(raw[s].size());
+            praw.resize(raw[s].size());
+            for (size_t i = 0; i < raw[s].size(); i++) {
+                keys[i] = L.dom_min + raw[s][i] % L.dom_size;
+                praw[i] = (uint32_t)(raw[s][i] / L.dom_size);
+            }
+        } else {
+            std::vector<uint32_t> state(L.capacity);
+            CUDA_TRY(cudaMemcpyAsync(state.data(), es.arena + L.off_state, L.capacity * 4, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaStreamSynchronize(es.st));
+            for (uint64_t i = 0; i < L.capacity; i++)
+                if (state[i] == ST_READY) raw[s].push_back((uint32_t)i);
+        }
+        if (L.capacity > FULL_COPY_MAX && !raw[s].empty()) {
+            CUDA_TRY(cudaMallocAsync((void**)&d_raw[s], raw[s].size() * 4, es.st));
+            es.temps.push_back(d_raw[s]);
+            CUDA_TRY(cudaMemcpyAsync(d_raw[s], raw[s].data(), raw[s].size() * 4, cudaMemcpyHostToDevice, es.st));
+        }
+        if (L.mode == SCOPE_HASH) {
+            int rc = fetch<uint64_t>(es, (const uint64_t*)(es.arena + L.off_keys), L.capacity, raw[s], d_raw[s], keys);
+            if (rc) return rc;
+            rc = fetch<uint32_t>(es, (const uint32_t*)(es.arena + L.off_parents), L.capacity, raw[s], d_raw[s], praw);
+            if (rc) return rc;
+        }
+        auto& S = res->scopes[s];
+        S.keys.resize(keys.size());
+        S.parents.resize(keys.size());
+        for (size_t i = 0; i < keys.size(); i++) {
+            S.keys[i] = nd.op == TAGG_OP_TERMS ? code_to_bits_h(nd.kind, keys[i]) : keys[i];
+            auto it = std::lower_bound(raw[ps].begin(), raw[ps].end(), praw[i]);
+            S.parents[i] = (uint32_t)(it - raw[ps].begin());
+        }
+    }
+    for (size_t k = 0; k < es.slots.size(); k++) {
+        const SlotLayout& SL = es.slots[k];
+        int node = m.slot_node[k];
+        const tagg_node& nd = m.nodes[node];
+        int s = m.scope_of[node];
+        auto& R = res->slots[k];
+        int rc = fetch<uint64_t>(es, (const uint64_t*)(es.arena + SL.off_acc), SL.capacity, raw[s], d_raw[s], R.values);
+        if (rc) return rc;
+        rc = fetch<uint8_t>(es, es.arena + SL.off_seen, SL.capacity, raw[s], d_raw[s], R.seen);
+        if (rc) return rc;
+        for (size_t i = 0; i < R.values.size(); i++) {
+            switch (nd.op) {
+                case TAGG_OP_COUNT: R.seen[i] = 1; break;
+                case TAGG_OP_SUM: break;  // accumulated in the natural type already
+                case TAGG_OP_MIN: R.values[i] = R.seen[i] ? code_to_bits_h(nd.kind, ~R.values[i]) : 0; break;
+                case TAGG_OP_MAX: R.values[i] = R.seen[i] ? code_to_bits_h(nd.kind, R.values[i]) : 0; break;
+            }
+            if (!R.seen[i] && nd.op != TAGG_OP_COUNT) R.values[i] = 0;
+        }
+    }
+    return read_percentiles(es, res);
+}
+
+// ---- PreparedAgg::merge on compact results --------------------------------------------------------
+static inline double bits_f64(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static inline uint64_t f64_bits(double d) { uint64_t b; memcpy(&b, &d, 8); return b; }
+static inline bool lt_bits(int kind, uint64_t a, uint64_t b) {
+    if (kind == TAGG_U64) return a < b;
+    if (kind == TAGG_F64) return bits_f64(a) < bits_f64(b);
+    return (int64_t)a < (int64_t)b;
+}
+
+struct PairHash {
+    size_t operator()(const std::pair<uint32_t, uint64_t>& p) const {
+        uint64_t z = p.second ^ ((uint64_t)p.first * 0x9E3779B97F4A7C15ull);
+        z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27;
+        return (size_t)z;
+    }
+};
+
+static void merge_pct(PctSummary& a, const PctSummary& b) {
+    if (b.n_total == 0) return;
+    if (a.n_total == 0) { a = b; return; }
+    // value order for f64 bits: compare as doubles (no NaN expected in percentile inputs)
+    auto less = [](uint64_t x, uint64_t y) { return bits_f64(x) < bits_f64(y); };
+    bool exact = a.ranks.size() == a.n_total && b.ranks.size() == b.n_total;
+    PctSummary o;
+    o.n_total = a.n_total + b.n_total;
+    if (exact) {  // both hold every element: an exact merge of two sorted lists
+        o.value_bits.resize(o.n_total);
+        std::merge(a.value_bits.begin(), a.value_bits.end(), b.value_bits.begin(), b.value_bits.end(), o.value_bits.begin(), less);
+        o.ranks.resize(o.n_total);
+        for (uint64_t i = 0; i < o.n_total; i++) o.ranks[i] = i + 1;
+    } else {
+        // rank of x in the union ~= rank_a(x) + (rank in b of the largest stored b-value <= x); the
+        // error is bounded by the gap between stored ranks of the other side (<= eps/4 relative)
+        struct E { uint64_t v, r; };
+        std::vector<E> out;
+        size_t j = 0;
+        uint64_t rb = 0;
+        for (size_t i = 0; i < a.ranks.size(); i++) {
+            while (j < b.ranks.size() && !less(a.value_bits[i], b.value_bits[j])) rb = b.ranks[j++];
+            out.push_back({a.value_bits[i], a.ranks[i] + rb});
+        }
+        j = 0;
+        uint64_t ra = 0;
+        for (size_t i = 0; i < b.ranks.size(); i++) {
+            while (j < a.ranks.size() && less(a.value_bits[j], b.value_bits[i])) ra = a.ranks[j++];
+            out.push_back({b.value_bits[i], b.ranks[i] + ra});
+        }
+        std::sort(out.begin(), out.end(), [&](const E& x, const E& y) { return x.r < y.r || (x.r == y.r && less(x.v, y.v)); });
+        for (auto& e : out) {
+            if (!o.ranks.empty() && o.ranks.back() == e.r) continue;
+            o.ranks.push_back(e.r);
+            o.value_bits.push_back(e.v);
+        }
+    }
+    a = std::move(o);
+}
+
+int result_merge(tagg_result* dst, const tagg_result* src) {
+    if (dst->meta.get() != src->meta.get() && dst->meta->nodes.size() != src->meta->nodes.size())
+        return tagg_fail(TAGG_ERR_BAD_ARG, "results come from different plans");
+    const PlanMeta& m = *dst->meta;
+    size_t ns = m.scope_node.size();
+    std::vector<std::vector<uint32_t>> map(ns);  // src bucket -> dst bucket, per scope
+    map[0] = {0};
+    for (size_t s = 1; s < ns; s++) {
+        auto& D = dst->scopes[s];
+        const auto& S = src->scopes[s];
+        int ps = m.scope_parent[s];
+        std::unordered_map<std::pair<uint32_t, uint64_t>, uint32_t, PairHash> index;
+        index.reserve(D.keys.size() * 2 + S.keys.size());
+        for (size_t i = 0; i < D.keys.size(); i++) index[{D.parents[i], D.keys[i]}] = (uint32_t)i;
+        map[s].resize(S.keys.size());
+        for (size_t i = 0; i < S.keys.size(); i++) {
+            uint32_t dp = map[ps][S.parents[i]];
+            auto key = std::make_pair(dp, S.keys[i]);
+            auto it = index.find(key);
+            if (it == index.end()) {  // or_insert_with(create_fruit)
+                uint32_t at = (uint32_t)D.keys.size();
+                D.keys.push_back(S.keys[i]);
+                D.parents.push_back(dp);
+                index[key] = at;
+                map[s][i] = at;
+            } else {
+                map[s][i] = it->second;
+            }
+        }
+    }
+    for (size_t k = 0; k < m.slot_node.size(); k++) {
+        int node = m.slot_node[k];
+        const tagg_node& nd = m.nodes[node];
+        int s = m.scope_of[node];
+        auto& D = dst->slots[k];
+        const auto& S = src->slots[k];
+        size_t nb = dst->scopes[s].keys.size();
+        D.values.resize(nb, 0);
+        D.seen.resize(nb, nd.op == TAGG_OP_COUNT ? 1 : 0);
+        for (size_t i = 0; i < S.values.size(); i++) {
+            uint32_t d = map[s][i];
+            if (nd.op == TAGG_OP_COUNT) { D.values[d] += S.values[i]; D.seen[d] = 1; continue; }
+            if (!S.seen[i]) continue;  // None => return
+            if (!D.seen[d]) { D.values[d] = S.values[i]; D.seen[d] = 1; continue; }  // acc.replace(v)
+            uint64_t v = S.values[i], &acc = D.values[d];
+            if (nd.op == TAGG_OP_SUM) acc = nd.kind == TAGG_F64 ? f64_bits(bits_f64(acc) + bits_f64(v)) : acc + v;
+            else if (nd.op == TAGG_OP_MIN) { if (lt_bits(nd.kind, v, acc)) acc = v; }
+            else { if (lt_bits(nd.kind, acc, v)) acc = v; }
+        }
+    }
+    for (size_t k = 0; k < m.pct_node.size(); k++) {
+        for (auto& kv : src->pcts[k]) merge_pct(dst->pcts[k][kv.first], kv.second);
+    }
+    dst->kernel_ms += src->kernel_ms;
+    dst->alg_bytes += src->alg_bytes;
+    dst->n_launches += src->n_launches;
+    return 0;
+}
+
+// ---- readers --------------------------------------------------------------------------------------
+static int scope_index(const tagg_result* res, uint32_t scope_node) {
+    if (scope_node == TAGG_ROOT_SCOPE) return 0;
+    if (scope_node >= res->meta->nodes.size() || res->meta->own_scope[scope_node] < 0) return -1;
+    return res->meta->own_scope[scope_node];
+}
+
+extern "C" {
+
+int tagg_result_scope_len(const tagg_result* res, uint32_t scope_node, uint64_t* n_buckets) {
+    if (!res || !n_buckets) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    int s = scope_index(res, scope_node);
+    if (s < 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
+    *n_buckets = res->scopes[s].keys.size();
+    return 0;
+}
+
+int tagg_result_scope_read(const tagg_result* res, uint32_t scope_node, uint64_t* keys, uint32_t* parents, uint64_t cap) {
+    if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    int s = scope_index(res, scope_node);
+    if (s < 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
+    const auto& S = res->scopes[s];
+    if (cap < S.keys.size()) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
+    if (keys && !S.keys.empty()) memcpy(keys, S.keys.data(), S.keys.size() * 8);
+    if (parents && !S.parents.empty()) memcpy(parents, S.parents.data(), S.parents.size() * 4);
+    return 0;
+}
+
+int tagg_result_metric_len(const tagg_result* res, uint32_t node, uint64_t* n_buckets) {
+    if (!res || !n_buckets) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
+        return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
+    *n_buckets = res->slots[res->meta->slot_of[node]].values.size();
+    return 0;
+}
+
+int tagg_result_metric_read(const tagg_result* res, uint32_t node, uint64_t* values, uint8_t* seen, uint64_t cap) {
+    if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
+        return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
+    const auto& S = res->slots[res->meta->slot_of[node]];
+    if (cap < S.values.size()) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
+    if (values && !S.values.empty()) memcpy(values, S.values.data(), S.values.size() * 8);
+    if (seen && !S.seen.empty()) memcpy(seen, S.seen.data(), S.seen.size());
+    return 0;
+}
+
+static const PctSummary* find_pct(const tagg_result* res, uint32_t node, uint64_t bucket) {
+    if (node >= res->meta->nodes.size() || res->meta->pct_of[node] < 0) return nullptr;
+    const auto& mp = res->pcts[res->meta->pct_of[node]];
+    auto it = mp.find(bucket);
+    static const PctSummary empty;
+    return it == mp.end() ? &empty : &it->second;
+}
+
+int tagg_result_percentiles_len(const tagg_result* res, uint32_t node, uint64_t bucket, uint64_t* n_total, uint64_t* n_pairs) {
+    if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    const PctSummary* p = find_pct(res, node, bucket);
+    if (!p) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a percentiles leaf", node);
+    if (n_total) *n_total = p->n_total;
+    if (n_pairs) *n_pairs = p->ranks.size();
+    return 0;
+}
+
+int tagg_result_percentiles_read(const tagg_result* res, uint32_t node, uint64_t bucket, uint64_t* ranks, uint64_t* value_bits,
+                                 uint64_t cap) {
+    if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    const PctSummary* p = find_pct(res, node, bucket);
+    if (!p) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a percentiles leaf", node);
+    if (cap < p->ranks.size()) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
+    if (ranks && !p->ranks.empty()) memcpy(ranks, p->ranks.data(), p->ranks.size() * 8);
+    if (value_bits && !p->value_bits.empty()) memcpy(value_bits, p->value_bits.data(), p->value_bits.size() * 8);
+    return 0;
+}
+
+int tagg_result_stats(const tagg_result* res, double* kernel_ms, uint64_t* alg_bytes, uint32_t* n_launches, uint32_t* path_used) {
+    if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    if (kernel_ms) *kernel_ms = res->kernel_ms;
+    if (alg_bytes) *alg_bytes = res->alg_bytes;
+    if (n_launches) *n_launches = res->n_launches;
+    if (path_used) *path_used = res->path_used;
+    return 0;
+}
+
+}  // extern "C"
