@@ -86,7 +86,7 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_d
             uint32_t* w = nullptr;
             int rc = dev_alloc(es, &w, words * 4);
             if (rc) return rc;
-            CUDA_TRY(cudaMemsetAsync(w + (words - 5), 0, 20, es.st));
+            { size_t tail = words >= 5 ? words - 5 : 0; CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st)); }
             if (need) CUDA_TRY(cudaMemcpyAsync(w, in.data, need, cudaMemcpyHostToDevice, es.st));
             d.kind = DS_BITSET;
             d.words = w;
