@@ -100,9 +100,11 @@ typedef enum tagg_docset_kind {
     TAGG_DOCSET_ALL = 0,        /* AllScorer: every doc in 0..max_doc                        */
     TAGG_DOCSET_BITSET = 1,     /* data = ceil(max_doc/8) bytes, doc d set iff data[d>>3]>>(d&7)&1 */
     TAGG_DOCSET_SORTED_IDS = 2, /* data = n strictly ascending uint32 doc ids                */
-    TAGG_DOCSET_COLUMN_RANGE = 3 /* docset produced on the device: docs whose single-valued fast
+    TAGG_DOCSET_COLUMN_RANGE = 3,/* docset produced on the device: docs whose single-valued fast
                                     field `field_id` has lo <= code <= hi (TermQuery / RangeQuery on
                                     an INDEXED|FAST field).  data = NULL.          */
+    TAGG_DOCSET_DEVICE_BITSET = 4 /* a bitset already resident in HBM: data = the device pointer
+                                    returned by tagg_docset_cache (reusable filters stay on the GPU) */
 } tagg_docset_kind;
 
 typedef struct tagg_docset {
@@ -140,6 +142,10 @@ int tagg_ctx_synchronize(tagg_ctx* ctx);
 /* Tuning/testing knob: 0 = let the planner choose (default), 1 = force the generic
  * tree-walking kernel, 2 = force the streaming kernels (error if the plan has no fast shape). */
 int tagg_ctx_set_path(tagg_ctx* ctx, int path);
+/* Device-side stopwatch (CUDA events on the stream executes run on): start, run K executes from the
+ * same host thread, stop -> elapsed milliseconds on the device timeline. */
+int tagg_ctx_timer_start(tagg_ctx* ctx);
+int tagg_ctx_timer_stop(tagg_ctx* ctx, double* ms);
 /* Number of kernels launched by this context so far (bench.py `gpu_launches`). */
 int tagg_ctx_launch_count(const tagg_ctx* ctx, uint64_t* out);
 
@@ -175,6 +181,16 @@ int tagg_column_info(const tagg_segment* seg, uint32_t field_id, int which,
                      uint64_t* n_values, uint64_t* packed_len);
 int tagg_column_download(const tagg_segment* seg, uint32_t field_id, int which,
                          uint8_t* out, size_t cap);
+
+/* ---- device-resident docsets (SURVEY §7 "PCIe handoff", §8f-1) ------------------------------
+ * tagg_docset_cache evaluates / uploads `in` once into a bitset owned by the segment and fills
+ * `out` with a TAGG_DOCSET_DEVICE_BITSET docset that later executes read straight from HBM (a
+ * reusable filter such as status=0).  Released by tagg_docset_uncache or with the segment.
+ * tagg_docset_to_bitset evaluates a docset on the device and returns the bitset bytes to the host
+ * (ceil(max_doc/8) bytes) — e.g. a TermQuery on an INDEXED|FAST field without touching postings. */
+int tagg_docset_cache(tagg_segment* seg, const tagg_docset* in, tagg_docset* out);
+int tagg_docset_uncache(tagg_segment* seg, const tagg_docset* cached);
+int tagg_docset_to_bitset(const tagg_segment* seg, const tagg_docset* in, uint8_t* out, size_t cap);
 
 /* ---- plans (replaces Agg::prepare -> PreparedAgg, agg.rs:10-28) ---------------------- */
 int tagg_plan_create(tagg_ctx* ctx, const tagg_node* nodes, uint32_t n_nodes,

@@ -15,7 +15,7 @@ U64, I64, F64, DATE = range(4)
 (OP_TUPLE, OP_COUNT, OP_SUM, OP_MIN, OP_MAX, OP_PERCENTILES, OP_TERMS, OP_HISTOGRAM, OP_FILTER,
  OP_POST_FILTER) = range(10)
 PRED_NONE, PRED_RANGE, PRED_LUT = range(3)
-DOCSET_ALL, DOCSET_BITSET, DOCSET_SORTED_IDS, DOCSET_COLUMN_RANGE = range(4)
+DOCSET_ALL, DOCSET_BITSET, DOCSET_SORTED_IDS, DOCSET_COLUMN_RANGE, DOCSET_DEVICE_BITSET = range(5)
 ROOT_SCOPE = 0xFFFFFFFF
 UNIQUE_ID_BYTES = 128
 PATH_AUTO, PATH_GENERIC, PATH_STREAM = 0, 1, 2
@@ -67,6 +67,11 @@ SYMBOLS = {
     "tagg_ctx_device": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "tagg_ctx_synchronize": (C.c_int, [_P]),
     "tagg_ctx_set_path": (C.c_int, [_P, C.c_int]),
+    "tagg_ctx_timer_start": (C.c_int, [_P]),
+    "tagg_ctx_timer_stop": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "tagg_docset_cache": (C.c_int, [_P, C.POINTER(Docset), C.POINTER(Docset)]),
+    "tagg_docset_uncache": (C.c_int, [_P, C.POINTER(Docset)]),
+    "tagg_docset_to_bitset": (C.c_int, [_P, C.POINTER(Docset), _P, C.c_size_t]),
     "tagg_ctx_launch_count": (C.c_int, [_P, _U64P]),
     "tagg_segment_create": (C.c_int, [_P, C.c_uint32, _PP]),
     "tagg_segment_destroy": (C.c_int, [_P]),

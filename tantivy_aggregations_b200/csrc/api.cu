@@ -176,6 +176,7 @@ int tagg_ctx_destroy(tagg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     tagg_comm_destroy(ctx);
     for (auto s : ctx->stream_pool) cudaStreamDestroy(s);
+    if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     delete ctx;
     return 0;
 }
@@ -196,6 +197,32 @@ int tagg_ctx_synchronize(tagg_ctx* ctx) {
 int tagg_ctx_set_path(tagg_ctx* ctx, int path) {
     if (!ctx || path < 0 || path > 2) return tagg_fail(TAGG_ERR_BAD_ARG, "bad path");
     ctx->path = path;
+    return 0;
+}
+
+int tagg_ctx_timer_start(tagg_ctx* ctx) {
+    if (!ctx) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->timer0) { CUDA_TRY(cudaEventCreate(&ctx->timer0)); CUDA_TRY(cudaEventCreate(&ctx->timer1)); }
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaStream_t st = ctx->acquire_stream();  // LIFO pool: the same stream the next execute will use
+    cudaError_t e = cudaEventRecord(ctx->timer0, st);
+    ctx->release_stream(st);
+    if (e != cudaSuccess) return tagg_fail(TAGG_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int tagg_ctx_timer_stop(tagg_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->timer0) return tagg_fail(TAGG_ERR_BAD_ARG, "timer not started");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->acquire_stream();
+    cudaError_t e = cudaEventRecord(ctx->timer1, st);
+    ctx->release_stream(st);
+    if (e != cudaSuccess) return tagg_fail(TAGG_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaEventSynchronize(ctx->timer1));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->timer0, ctx->timer1));
+    *ms = f;
     return 0;
 }
 

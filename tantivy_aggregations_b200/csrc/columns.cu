@@ -225,6 +225,7 @@ int tagg_segment_destroy(tagg_segment* seg) {
     for (auto& kv : seg->cols) column_free(&kv.second);
     for (auto& kv : seg->mcols) { column_free(&kv.second.first); column_free(&kv.second.second); }
     if (seg->d_deleted) cudaFree(seg->d_deleted);
+    for (auto p : seg->cached_bitsets) cudaFree(p);
     delete seg;
     return 0;
 }
@@ -314,7 +315,7 @@ int tagg_segment_set_deletes(tagg_segment* seg, const uint8_t* bytes, size_t len
     size_t need = ((size_t)seg->max_doc + 7) / 8;
     if (len < need) return tagg_fail(TAGG_ERR_BAD_ARG, "delete bitset needs %zu bytes, got %zu", need, len);
     CUDA_TRY(cudaSetDevice(seg->ctx->device));
-    size_t words = ((size_t)seg->max_doc + 31) / 32 + 4;
+    size_t words = (((size_t)seg->max_doc + TAGG_TILE_DOCS - 1) / TAGG_TILE_DOCS) * (TAGG_TILE_DOCS / 32) + 16;
     if (seg->d_deleted) { cudaFree(seg->d_deleted); seg->d_deleted = nullptr; }
     CUDA_TRY(cudaMalloc(&seg->d_deleted, words * 4));
     CUDA_TRY(cudaMemset(seg->d_deleted, 0, words * 4));

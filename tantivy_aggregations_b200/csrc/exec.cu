@@ -73,7 +73,7 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_d
     DevDocset d;
     memset(&d, 0, sizeof(d));
     size_t need = ((size_t)seg->max_doc + 7) / 8;
-    size_t words = ((size_t)seg->max_doc + 31) / 32 + 4;
+    size_t words = (((size_t)seg->max_doc + TAGG_TILE_DOCS - 1) / TAGG_TILE_DOCS) * (TAGG_TILE_DOCS / 32) + 16;
     switch (in.kind) {
         case TAGG_DOCSET_ALL:
             d.kind = DS_ALL;
@@ -86,10 +86,20 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_d
             uint32_t* w = nullptr;
             int rc = dev_alloc(es, &w, words * 4);
             if (rc) return rc;
-            { size_t tail = words >= 5 ? words - 5 : 0; CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st)); }
+            { size_t tail = need / 4; CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st)); }
             if (need) CUDA_TRY(cudaMemcpyAsync(w, in.data, need, cudaMemcpyHostToDevice, es.st));
             d.kind = DS_BITSET;
             d.words = w;
+            if (n_cand) *n_cand = seg->max_doc;
+            es.alg_bytes += need;
+            break;
+        }
+        case TAGG_DOCSET_DEVICE_BITSET: {
+            bool known = false;
+            for (auto p : seg->cached_bitsets) known = known || p == in.data;
+            if (!known) return tagg_fail(TAGG_ERR_BAD_ARG, "device bitset was not created by tagg_docset_cache on this segment");
+            d.kind = DS_BITSET;
+            d.words = (const uint32_t*)in.data;
             if (n_cand) *n_cand = seg->max_doc;
             es.alg_bytes += need;
             break;

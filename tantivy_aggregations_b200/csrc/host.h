@@ -32,6 +32,7 @@ struct tagg_ctx {
     std::atomic<uint64_t> launches{0};
     std::mutex mu;
     std::vector<cudaStream_t> stream_pool;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     // NCCL (comm.cu), loaded lazily with dlopen so that single-GPU use has no NCCL dependency
     void* nccl = nullptr;  // opaque NcclState*
     int rank = 0, n_ranks = 1;
@@ -67,6 +68,8 @@ struct tagg_segment {
     uint32_t* d_deleted = nullptr;
     bool has_deletes = false;
     uint64_t n_deleted = 0;
+    std::vector<uint32_t*> cached_bitsets;  // tagg_docset_cache allocations
+    std::mutex mu;
 };
 
 // Derived, immutable description of a plan (shared with its results).

@@ -37,6 +37,14 @@ class Context:
     def synchronize(self):
         F.check(F.lib().tagg_ctx_synchronize(self._h))
 
+    def timer_start(self):
+        F.check(F.lib().tagg_ctx_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        F.check(F.lib().tagg_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         n = C.c_uint64()
         F.check(F.lib().tagg_ctx_launch_count(self._h, C.byref(n)))
@@ -152,6 +160,21 @@ class Segment:
         F.check(F.lib().tagg_segment_set_deletes(self._h, _ptr(buf), len(buf)))
         self.deletes = bytes(raw)
 
+    # -- device-resident docsets -------------------------------------------------------------
+    def cache_docset(self, docset):
+        """Evaluate / upload a docset once; returns a Docset (DEVICE_BITSET) reusable across queries."""
+        out = F.Docset()
+        F.check(F.lib().tagg_docset_cache(self._h, C.byref(docset.c), C.byref(out)))
+        d = Docset.__new__(Docset)
+        d.buf, d.c = None, out
+        return d
+
+    def docset_to_bitset(self, docset):
+        """Evaluate a docset on the device and return its bitset bytes (np.uint8)."""
+        out = np.zeros((self.max_doc + 7) // 8, dtype=np.uint8)
+        F.check(F.lib().tagg_docset_to_bitset(self._h, C.byref(docset.c), _ptr(out), len(out)))
+        return out
+
     # -- introspection ---------------------------------------------------------------------
     def column_info(self, field, which=0):
         mn, amp, nv, pl = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -210,6 +233,16 @@ class BitsetQuery(Query):
         raw = self.per_segment[seg.ord]
         buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
         return Docset(F.DOCSET_BITSET, buf, len(buf))
+
+
+class CachedQuery(Query):
+    """A query whose per-segment docsets were made device-resident once (Segment.cache_docset)."""
+
+    def __init__(self, query, segments):
+        self.per_segment = {seg.ord: seg.cache_docset(query.docset(seg)) for seg in segments}
+
+    def docset(self, seg):
+        return self.per_segment[seg.ord]
 
 
 class DocIdsQuery(Query):

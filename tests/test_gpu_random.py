@@ -177,3 +177,39 @@ def test_percentiles_small_n_exact(ctx):
     # empty -> None
     corpus = Corpus([SegSpec(0).col(PRICE, F.F64, np.zeros(0))])
     assert corpus.build_gpu(ctx).agg_search(ta.AllQuery(), ta.percentiles_agg_f64(PRICE)).percentile(0.5) is None
+
+
+STREAM_SHAPES = ["scalars", "terms", "terms_i64", "terms_const", "bench_shape", "hist", "hist_fine", "post_filter",
+                 "post_filter_f64", "post_filter_lut"]
+
+
+@pytest.mark.parametrize("qname", ["all", "bitset", "range_dev"])
+@pytest.mark.parametrize("aname", STREAM_SHAPES)
+def test_streaming_kernel_is_used_and_matches_generic(ctx, world, qname, aname):
+    """The flat shapes run on the TMA-staged streaming kernel (path 2); forcing the generic
+    tree-walking kernel (path 1) must give the same fruit, and both equal the oracle."""
+    corpus, searcher, ox = world
+    q = queries(corpus, 5)[qname]
+    want, _, _ = ox.search(q, aggs()[aname]())
+    ctx.set_path(F.PATH_STREAM)
+    try:
+        got, reader = searcher.agg_search_with_executor(q, aggs()[aname](), ta.SINGLE_THREAD, return_reader=True)
+        assert reader.stats()["path"] == 2
+    finally:
+        ctx.set_path(F.PATH_AUTO)
+    assert_fruit_equal(got, want, F64_SUM_RTOL)
+
+
+def test_cached_device_docsets(ctx, world):
+    """Reusable filters kept resident in HBM (tagg_docset_cache) and docsets produced on the device
+    (tagg_docset_to_bitset) agree with the host-evaluated ones."""
+    corpus, searcher, ox = world
+    host_q = ta.RangeQuery(STATUS, F.U64, 0, 0, device=False)
+    for seg in searcher.segments:
+        dev_bits = seg.docset_to_bitset(ta.RangeQuery(STATUS, F.U64, 0, 0).docset(seg))
+        assert (dev_bits == host_q.docset(seg).buf).all()
+    cached = ta.CachedQuery(host_q, searcher.segments)
+    agg = lambda fq: ta.filter_agg(fq, (ta.count_agg(), ta.terms_agg_u64(CAT, (ta.count_agg(), ta.min_agg_f64(PRICE)))))
+    want, _, _ = ox.search(ta.AllQuery(), agg(host_q))
+    assert_fruit_equal(searcher.agg_search(ta.AllQuery(), agg(cached)), want)
+    assert_fruit_equal(searcher.agg_search(cached, ta.count_agg()), ox.search(host_q, ta.count_agg())[0])
