@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=100_000_000, help="documents per GPU (default: the C2 size)")
     ap.add_argument("--segments", type=int, default=8)
-    ap.add_argument("--cpu-sample-segments", type=int, default=4, help="segments of the workload the CPU baseline runs on")
+    ap.add_argument("--cpu-sample-segments", type=int, default=8, help="segments of the workload the CPU baseline runs on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 force generic kernel, 2 force streaming kernel")
     return ap.parse_args()
@@ -70,6 +70,7 @@ class ClockSampler:
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        time.sleep(0.5)  # let the first samples land before the timed region starts
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}

@@ -31,7 +31,7 @@
 #define ST_MAXCOLS 6
 #define ST_MAXPRED 4
 #define ST_MAXBITS (2 + ST_MAXPRED)
-#define ST_MAXRG 2
+#define ST_MAXRG 4
 #define ST_MAXBG 3
 
 enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2, PR_MAIN_RANGE = 3, PR_FILTER_RANGE = 4 };
