@@ -7,26 +7,33 @@
 // copies (cp.async.bulk + mbarrier) through a 3-stage ring, so HBM is read exactly once, fully
 // coalesced, while the SM unpacks the previous tile from shared memory.
 //
-// Per tile each warp owns 128 documents: it folds the bitsets and the value predicates into a 32-bit
-// match mask per word (ballot), COMPACTS the matching document indices into a per-warp queue, and
-// only then unpacks key / value columns for matched documents — so a 25 %-selective filter costs a
-// quarter of the unpack and table instructions (the reference pays a hash probe per matched doc,
-// terms.rs:127-132; the doc stream narrowing is filter.rs:100-122 / post_filter.rs:245-249).
+// Per tile each warp owns 256 documents = 8 bitset words:
+//   phase 1  lanes 0..7 AND the staged bitset words (docset, ~deletes, filter docsets) of "their"
+//            word into a match mask; value predicates (post_filter / COLUMN_RANGE) are evaluated per
+//            document and folded in with ballots;
+//   phase 2  the set bits are COMPACTED into a per-warp queue of document indices (warp scan of the
+//            popcounts + one predicated shared store per word);
+//   phase 3  full warps drain the queue: only matched documents pay the unpack of key / value
+//            columns and the table updates (the reference pays a hash probe per matched doc,
+//            terms.rs:127-132; the doc-stream narrowing is filter.rs:100-122 / post_filter.rs:245-249).
+// With nothing narrowing the doc stream (AllQuery, no deletes) phase 2 is skipped.
 //
 // Root metrics live in registers and are reduced by warp shuffles; bucket metrics go to dense tables
 // in global memory (L2-resident): counts / sums with RED atomics, min / max with a cached
 // check-before-atomic (cells only move monotonically, so a stale read can only cause a redundant
-// atomic, never a wrong skip).
+// atomic, never a wrong skip).  The kernel is a template over the number of root / bucket column
+// groups so every per-tile column descriptor lives in registers.
 #include <string.h>
 
 #include <algorithm>
 
 #include "exec.h"
 
-#define ST_THREADS 512
+#define ST_THREADS 256
 #define ST_WARPS (ST_THREADS / 32)
 #define ST_TILE TAGG_TILE_DOCS
-#define ST_WORDS_PER_WARP (ST_TILE / 32 / ST_WARPS)  // 4
+#define ST_WORDS_PER_WARP (ST_TILE / 32 / ST_WARPS)  // 8
+#define ST_DOCS_PER_WARP (ST_WORDS_PER_WARP * 32)    // 256
 #define ST_STAGES 3
 #define ST_MAXCOLS 6
 #define ST_MAXPRED 4
@@ -34,49 +41,49 @@
 #define ST_MAXRG 4
 #define ST_MAXBG 3
 
-enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2, PR_MAIN_RANGE = 3, PR_FILTER_RANGE = 4 };
+enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2 };
 enum { OPB_SUM = 1, OPB_MIN = 2, OPB_MAX = 4 };
 enum { BK_NONE = 0, BK_TERMS = 1, BK_HIST = 2 };
+enum { SF_MAIN_BITS = 1, SF_DELETES = 2, SF_PRED_BITS0 = 4 /* << i */, SF_PRED_NONE0 = 256 /* << i */ };
 
-struct SPred {
-    int32_t type;
-    int32_t scol;     // staged column (RANGE / LUT)
-    int32_t filter;   // FILTER: index into DevSegment.filters
-    uint32_t pad;
-    uint64_t lo, hi;  // RANGE: inclusive code range; LUT: base, number of bits
-    const uint8_t* lut;
+// Everything the kernel needs to know about one segment, prepared on the host.
+struct SegDesc {
+    uint32_t tile_begin, max_doc, flags, pad;
+    const uint8_t* col_ptr[ST_MAXCOLS];
+    uint64_t minv[ST_MAXCOLS];
+    uint32_t nb[ST_MAXCOLS];
+    const uint8_t* bits_ptr[ST_MAXBITS];  // 0 = main docset, 1 = deleted, 2+i = filter docset of pred i
+    uint64_t pred_lo[ST_MAXPRED], pred_hi[ST_MAXPRED];
 };
 struct SGroup {
     int32_t scol;
     uint32_t kind;
     uint32_t ops;
-    uint32_t slot_sum, slot_min, slot_max;
+    uint32_t pad;
+    uint64_t *acc_sum, *acc_min, *acc_max;
+    uint8_t *seen_sum, *seen_min, *seen_max;
 };
 struct SParams {
-    const DevSegment* segs;
-    const uint32_t* tile_prefix;  // n_segs + 1
-    const DevPlan* P;
+    const SegDesc* segs;
     uint32_t n_segs, n_tiles;
     int32_t n_cols;
-    int32_t col_slot[ST_MAXCOLS];   // staged column -> DevSegment.cols index
-    uint32_t soff_col[ST_MAXCOLS];  // byte offset inside a stage
-    uint32_t soff_bits;             // first bitset slot inside a stage (256 B each): 0 = main, 1 = deleted, 2+i = pred i
+    uint32_t soff_col[ST_MAXCOLS];  // byte offset of each staged column inside a stage
+    uint32_t soff_bits;             // bitset slots (256 B each) inside a stage
     uint32_t stage_bytes;
     int32_t n_preds;
-    SPred preds[ST_MAXPRED];
+    int32_t pred_type[ST_MAXPRED];
+    int32_t pred_scol[ST_MAXPRED];
+    const uint8_t* pred_lut[ST_MAXPRED];
     int32_t n_root_counts;
-    uint32_t root_count_slots[2];
-    int32_t n_rgroups;
+    uint64_t* root_count_acc[2];
     SGroup rgroups[ST_MAXRG];
-    int32_t bucket_mode, key_scol;
+    int32_t key_scol;
     uint64_t dom_min, dom_size;
     double f0, f1;
-    uint8_t* present;
+    uint8_t* present;  // nullptr: derived from the bucket counts after the kernel
     int32_t n_bcounts;
-    uint32_t bcount_slots[2];
-    int32_t n_bgroups;
+    uint64_t* bcount_acc[2];
     SGroup bgroups[ST_MAXBG];
-    int32_t compact;
 };
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy ---------------------------------------------------------
@@ -86,6 +93,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
@@ -105,139 +115,84 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-// value i of a staged column tile (tantivy BitUnpacker::get on shared memory, 32-bit aligned loads)
-__device__ __forceinline__ uint64_t sunpack(const uint32_t* __restrict__ s32, uint32_t nb, uint64_t mask, uint32_t i) {
-    uint32_t bit = i * nb;
+// A staged column of the current tile, held in registers.
+struct TCol {
+    const uint32_t* s32;
+    uint64_t minv, mask;
+    uint32_t nb;
+};
+__device__ __forceinline__ TCol tcol(const SParams& p, const SegDesc* S, const uint8_t* stage, int scol) {
+    TCol c;
+    c.s32 = (const uint32_t*)(stage + p.soff_col[scol]);
+    c.nb = S->nb[scol];
+    c.minv = S->minv[scol];
+    c.mask = c.nb == 64 ? ~0ull : ((1ull << c.nb) - 1ull);
+    return c;
+}
+// value i of a staged column tile (tantivy BitUnpacker::get on shared memory, 32-bit aligned loads) -> code
+__device__ __forceinline__ uint64_t tget(const TCol& c, uint32_t i) {
+    uint32_t bit = i * c.nb;
     uint32_t wi = bit >> 5, sh = bit & 31u;
-    uint32_t w0 = s32[wi], w1 = s32[wi + 1];
+    uint32_t w0 = c.s32[wi], w1 = c.s32[wi + 1];
     uint32_t lo = __funnelshift_r(w0, w1, sh);
     uint32_t hi = 0;
-    if (nb > 32) {
-        uint32_t w2 = s32[wi + 2];
+    if (c.nb > 32) {
+        uint32_t w2 = c.s32[wi + 2];
         hi = __funnelshift_r(w1, w2, sh);
     }
-    return (((uint64_t)hi << 32) | lo) & mask;
+    return ((((uint64_t)hi << 32) | lo) & c.mask) + c.minv;
 }
 
-struct TileCtx {
-    const uint8_t* stage;
-    const DevSegment* S;
-    uint32_t nb[ST_MAXCOLS];
-    uint64_t mask[ST_MAXCOLS];
-    uint64_t minv[ST_MAXCOLS];
-};
-
-__device__ __forceinline__ uint64_t tile_code(const SParams& p, const TileCtx& t, int scol, uint32_t dl) {
-    return sunpack((const uint32_t*)(t.stage + p.soff_col[scol]), t.nb[scol], t.mask[scol], dl) + t.minv[scol];
-}
-
+template <int BUCKET, int NBG, int NRG, bool COMPACT>
 __global__ void __launch_bounds__(ST_THREADS) k_stream(const __grid_constant__ SParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;
     uint16_t* queues = (uint16_t*)(smem + (size_t)ST_STAGES * p.stage_bytes);
-    uint64_t* full = (uint64_t*)(queues + ST_WARPS * ST_WORDS_PER_WARP * 32);
+    uint64_t* full = (uint64_t*)(queues + ST_WARPS * ST_DOCS_PER_WARP);
     uint32_t* stage_seg = (uint32_t*)(full + ST_STAGES);  // [stage] = segment, [ST_STAGES + stage] = local tile
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     if (tid == 0) {
         for (int s = 0; s < ST_STAGES; s++) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // thread 0 is the producer: locate the tile, arm the stage's barrier with the byte count, issue the copies
+    // thread 0 is the producer: tiles are visited in ascending order, so the segment cursor only advances
+    uint32_t cur_seg = 0;
     auto issue = [&](uint32_t tile, int stage) {
-        uint32_t lo = 0, hi = p.n_segs;  // last seg with prefix <= tile
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
-        }
-        const DevSegment* S = p.segs + lo;
-        uint32_t lt = tile - p.tile_prefix[lo];
-        stage_seg[stage] = lo;
+        while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= tile) cur_seg++;
+        const SegDesc* S = p.segs + cur_seg;
+        uint32_t lt = tile - S->tile_begin;
+        stage_seg[stage] = cur_seg;
         stage_seg[ST_STAGES + stage] = lt;
         uint8_t* base = stages + (size_t)stage * p.stage_bytes;
+        uint32_t flags = S->flags;
         uint32_t bytes = 0;
-        for (int c = 0; c < p.n_cols; c++) bytes += (ST_TILE / 8) * S->cols[p.col_slot[c]].num_bits;
-        if (S->main.kind == DS_BITSET) bytes += ST_TILE / 8;
-        if (S->has_deletes) bytes += ST_TILE / 8;
-        for (int i = 0; i < p.n_preds; i++)
-            if (p.preds[i].type == PR_FILTER && S->filters[p.preds[i].filter].kind == DS_BITSET) bytes += ST_TILE / 8;
-        if (bytes == 0) {  // nothing to stage (e.g. count over AllQuery): complete the phase by hand
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + stage)) : "memory");
+        for (int c = 0; c < p.n_cols; c++) bytes += (ST_TILE / 8) * S->nb[c];
+        bytes += (ST_TILE / 8) * __popc(flags & 0xffu);
+        if (bytes == 0) {  // nothing to stage (count over AllQuery): complete the phase by hand
+            mbar_arrive(full + stage);
             return;
         }
         mbar_expect_tx(full + stage, bytes);
         for (int c = 0; c < p.n_cols; c++) {
-            const DevColumn& col = S->cols[p.col_slot[c]];
-            uint32_t cb = (ST_TILE / 8) * col.num_bits;
-            if (cb) tma_bulk_g2s(base + p.soff_col[c], (const uint8_t*)col.words + (size_t)lt * cb, cb, full + stage);
+            uint32_t cb = (ST_TILE / 8) * S->nb[c];
+            if (cb) tma_bulk_g2s(base + p.soff_col[c], S->col_ptr[c] + (size_t)lt * cb, cb, full + stage);
         }
         uint8_t* bits = base + p.soff_bits;
-        if (S->main.kind == DS_BITSET) tma_bulk_g2s(bits, (const uint8_t*)S->main.words + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
-        if (S->has_deletes) tma_bulk_g2s(bits + 256, (const uint8_t*)S->deleted + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
-        for (int i = 0; i < p.n_preds; i++)
-            if (p.preds[i].type == PR_FILTER && S->filters[p.preds[i].filter].kind == DS_BITSET)
-                tma_bulk_g2s(bits + 512 + 256 * i, (const uint8_t*)S->filters[p.preds[i].filter].words + (size_t)lt * (ST_TILE / 8),
-                             ST_TILE / 8, full + stage);
+        for (int b = 0; b < ST_MAXBITS; b++)
+            if (flags & (1u << b)) tma_bulk_g2s(bits + 256 * b, S->bits_ptr[b] + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
     };
 
     // per-thread root accumulators
-    uint64_t rsum[ST_MAXRG], rmin[ST_MAXRG], rmax[ST_MAXRG];
+    uint64_t rsum[NRG ? NRG : 1], rmin[NRG ? NRG : 1], rmax[NRG ? NRG : 1];
     bool rseen = false;
 #pragma unroll
-    for (int g = 0; g < ST_MAXRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
-    uint64_t matched = 0;  // lane 0 only
+    for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
+    uint32_t matched = 0;  // every lane holds the warp's count
 
-    auto heavy = [&](const TileCtx& t, uint32_t dl) {
-        rseen = true;
-#pragma unroll
-        for (int g = 0; g < ST_MAXRG; g++) {
-            if (g < p.n_rgroups) {
-                const SGroup& G = p.rgroups[g];
-                uint64_t code = tile_code(p, t, G.scol, dl);
-                if (G.ops & OPB_SUM) {
-                    if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
-                    else rsum[g] += code_to_bits(G.kind, code);
-                }
-                if (G.ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
-                if (G.ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
-            }
-        }
-        if (p.bucket_mode != BK_NONE) {
-            uint64_t key = tile_code(p, t, p.key_scol, dl);
-            if (p.bucket_mode == BK_HIST) {
-                if (!hist_ord(key, p.f0, p.f1, &key)) return;  // NaN or below start: skipped (histogram.rs:138-145)
-            }
-            uint64_t rel = key - p.dom_min;
-            if (key < p.dom_min || rel >= p.dom_size) return;
-            if (!p.present[rel]) p.present[rel] = 1;
-            for (int c = 0; c < p.n_bcounts; c++) atomicAdd((unsigned long long*)(p.P->slots[p.bcount_slots[c]].acc + rel), 1ull);
-#pragma unroll
-            for (int g = 0; g < ST_MAXBG; g++) {
-                if (g < p.n_bgroups) {
-                    const SGroup& G = p.bgroups[g];
-                    uint64_t code = tile_code(p, t, G.scol, dl);
-                    if (G.ops & OPB_SUM) {
-                        uint64_t* a = p.P->slots[G.slot_sum].acc + rel;
-                        if (G.kind == TAGG_F64) atomicAdd((double*)a, code_to_f64(code));
-                        else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code));
-                    }
-                    if (G.ops & OPB_MIN) {
-                        uint64_t* a = p.P->slots[G.slot_min].acc + rel;
-                        uint64_t v = ~code;
-                        if (*a < v) atomicMax((unsigned long long*)a, (unsigned long long)v);
-                    }
-                    if (G.ops & OPB_MAX) {
-                        uint64_t* a = p.P->slots[G.slot_max].acc + rel;
-                        if (*a < code) atomicMax((unsigned long long*)a, (unsigned long long)code);
-                    }
-                }
-            }
-        }
-    };
-
-    // prologue: fill ST_STAGES-1 stages
     uint32_t my_first = blockIdx.x, step = gridDim.x;
     if (tid == 0) {
         for (int s = 0; s < ST_STAGES - 1; s++) {
@@ -247,83 +202,154 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream(const __grid_constant__ S
     }
     uint32_t k = 0;
     for (uint64_t tile = my_first; tile < p.n_tiles; tile += step, k++) {
-        int stage = k % ST_STAGES;
-        uint32_t parity = (k / ST_STAGES) & 1u;
+        const int stage = k % ST_STAGES;
+        const uint32_t parity = (k / ST_STAGES) & 1u;
         if (tid == 0) {
             uint64_t nt = tile + (uint64_t)(ST_STAGES - 1) * step;
             if (nt < p.n_tiles) issue((uint32_t)nt, (k + ST_STAGES - 1) % ST_STAGES);
         }
         mbar_wait(full + stage, parity);
 
-        TileCtx t;
-        t.stage = stages + (size_t)stage * p.stage_bytes;
-        t.S = p.segs + stage_seg[stage];
-        const DevSegment& S = *t.S;
+        const uint8_t* sbase = stages + (size_t)stage * p.stage_bytes;
+        const SegDesc* S = p.segs + stage_seg[stage];
         const uint32_t lt = stage_seg[ST_STAGES + stage];
-#pragma unroll
-        for (int c = 0; c < ST_MAXCOLS; c++) {
-            if (c < p.n_cols) {
-                const DevColumn& col = S.cols[p.col_slot[c]];
-                t.nb[c] = col.num_bits; t.mask[c] = col.mask; t.minv[c] = col.min_value;
+        const uint32_t flags = S->flags;
+        const uint32_t* bits = (const uint32_t*)(sbase + p.soff_bits);
+        // documents of this tile that exist
+        const uint64_t tile_doc0 = (uint64_t)lt * ST_TILE;
+        const uint32_t n_valid = (uint32_t)min((uint64_t)ST_TILE, (uint64_t)S->max_doc - tile_doc0);
+
+        // ---- phase 1: one match-mask word per lane (lanes 0..7) ------------------------------------
+        uint32_t m = 0;
+        if (lane < ST_WORDS_PER_WARP) {
+            uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
+            uint32_t d0 = wi * 32;
+            m = d0 + 32 <= n_valid ? 0xffffffffu : (d0 >= n_valid ? 0u : ((1u << (n_valid - d0)) - 1u));
+            if (flags & SF_MAIN_BITS) m &= bits[wi];
+            if (flags & SF_DELETES) m &= ~bits[64 + wi];  // searcher.rs:41-46
+            for (int i = 0; i < p.n_preds; i++) {
+                if (flags & (SF_PRED_BITS0 << i)) m &= bits[128 + 64 * i + wi];
+                if (flags & (SF_PRED_NONE0 << i)) m = 0;
             }
         }
-        const uint32_t* bits = (const uint32_t*)(t.stage + p.soff_bits);
-        uint16_t* q = queues + warp * (ST_WORDS_PER_WARP * 32);
-        uint32_t nq = 0;
+        // value predicates: evaluated per document, folded in with ballots
+        for (int i = 0; i < p.n_preds; i++) {
+            const int type = p.pred_type[i];
+            if (type == PR_FILTER) continue;
+            const TCol pc = tcol(p, S, sbase, p.pred_scol[i]);
+            const uint64_t lo = S->pred_lo[i], hi = S->pred_hi[i];
+            const uint8_t* lut = p.pred_lut[i];
 #pragma unroll
-        for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-            uint32_t wi = warp * ST_WORDS_PER_WARP + j;
-            uint32_t dl = wi * 32 + lane;                 // doc index inside the tile
-            uint64_t base_doc = (uint64_t)lt * ST_TILE + (uint64_t)wi * 32;
-            uint32_t m;
-            if (base_doc + 32 <= S.max_doc) m = 0xffffffffu;
-            else if (base_doc >= S.max_doc) m = 0;
-            else m = (1u << (uint32_t)(S.max_doc - base_doc)) - 1u;
-            if (S.main.kind == DS_BITSET) m &= bits[wi];
-            if (S.has_deletes) m &= ~bits[64 + wi];   // searcher.rs:41-46
-            for (int i = 0; i < p.n_preds && m; i++) {
-                const SPred& pr = p.preds[i];
-                if (pr.type == PR_FILTER) {
-                    const DevDocset& fd = S.filters[pr.filter];
-                    if (fd.kind == DS_BITSET) m &= bits[128 + 64 * i + wi];
-                    else if (fd.kind != DS_ALL) m = 0;
-                } else {
-                    uint64_t lo = pr.lo, hi = pr.hi;
-                    if (pr.type == PR_MAIN_RANGE) { lo = S.main.lo; hi = S.main.hi; }
-                    else if (pr.type == PR_FILTER_RANGE) { lo = S.filters[pr.filter].lo; hi = S.filters[pr.filter].hi; }
-                    uint64_t code = tile_code(p, t, pr.scol, dl);
+            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                if (mj) {
+                    uint64_t code = tget(pc, warp * ST_DOCS_PER_WARP + j * 32 + lane);
                     bool ok;
-                    if (pr.type == PR_LUT) {
+                    if (type == PR_LUT) {
                         uint64_t r = code - lo;
-                        ok = code >= lo && r < hi && ((pr.lut[r >> 3] >> (r & 7)) & 1);
+                        ok = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
                     } else {
                         ok = code >= lo && code <= hi;
                     }
-                    m &= __ballot_sync(0xffffffffu, ok);
+                    mj &= __ballot_sync(0xffffffffu, ok);
+                    if (lane == j) m = mj;
                 }
             }
-            if (lane == 0) matched += __popc(m);
-            if (p.compact) {
-                if ((m >> lane) & 1u) q[nq + __popc(m & ((1u << lane) - 1u))] = (uint16_t)dl;
-                nq += __popc(m);
-            } else if ((m >> lane) & 1u) {
-                heavy(t, dl);
-            }
         }
-        if (p.compact) {
+
+        // per-tile column descriptors of the roles this instantiation has, in registers
+        TCol kc, bc[NBG ? NBG : 1], rc[NRG ? NRG : 1];
+        if (BUCKET != BK_NONE) kc = tcol(p, S, sbase, p.key_scol);
+#pragma unroll
+        for (int g = 0; g < NBG; g++) bc[g] = tcol(p, S, sbase, p.bgroups[g].scol);
+#pragma unroll
+        for (int g = 0; g < NRG; g++) rc[g] = tcol(p, S, sbase, p.rgroups[g].scol);
+
+        auto heavy = [&](uint32_t dl) {
+            rseen = true;
+#pragma unroll
+            for (int g = 0; g < NRG; g++) {
+                const SGroup& G = p.rgroups[g];
+                if (G.ops) {
+                    uint64_t code = tget(rc[g], dl);
+                    if (G.ops & OPB_SUM) {
+                        if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
+                        else rsum[g] += code_to_bits(G.kind, code);
+                    }
+                    if (G.ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
+                    if (G.ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
+                }
+            }
+            if (BUCKET != BK_NONE) {
+                uint64_t key = tget(kc, dl);
+                if (BUCKET == BK_HIST) {
+                    if (!hist_ord(key, p.f0, p.f1, &key)) return;  // NaN or below start: skipped (histogram.rs:138-145)
+                }
+                uint64_t rel = key - p.dom_min;
+                if (key < p.dom_min || rel >= p.dom_size) return;
+                if (p.present && !p.present[rel]) p.present[rel] = 1;
+                if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel), 1ull);
+                if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel), 1ull);
+#pragma unroll
+                for (int g = 0; g < NBG; g++) {
+                    const SGroup& G = p.bgroups[g];
+                    uint64_t code = tget(bc[g], dl);
+                    if (G.ops & OPB_SUM) {
+                        if (G.kind == TAGG_F64) atomicAdd((double*)(G.acc_sum + rel), code_to_f64(code));
+                        else atomicAdd((unsigned long long*)(G.acc_sum + rel), (unsigned long long)code_to_bits(G.kind, code));
+                    }
+                    if (G.ops & OPB_MIN) {
+                        uint64_t v = ~code;
+                        if (G.acc_min[rel] < v) atomicMax((unsigned long long*)(G.acc_min + rel), (unsigned long long)v);
+                    }
+                    if (G.ops & OPB_MAX) {
+                        if (G.acc_max[rel] < code) atomicMax((unsigned long long*)(G.acc_max + rel), (unsigned long long)code);
+                    }
+                }
+            }
+        };
+
+        if (COMPACT) {
+            // ---- phase 2: compact the set bits of the 8 words into the warp's queue ------------------
+            uint32_t incl = __popc(m);
+#pragma unroll
+            for (int o = 1; o < ST_WORDS_PER_WARP; o <<= 1) {
+                uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            const uint32_t excl = incl - __popc(m);
+            const uint32_t nq = __shfl_sync(0xffffffffu, incl, ST_WORDS_PER_WARP - 1);
+            uint16_t* q = queues + warp * ST_DOCS_PER_WARP;
+#pragma unroll
+            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                uint32_t oj = __shfl_sync(0xffffffffu, excl, j);
+                if ((mj >> lane) & 1u) q[oj + __popc(mj & lt_mask)] = (uint16_t)(j * 32 + lane);
+            }
+            matched += nq;
             __syncwarp();
-            for (uint32_t jj = lane; jj < nq; jj += 32) heavy(t, q[jj]);
+            // ---- phase 3: full warps drain the queue --------------------------------------------------
+            for (uint32_t jj = lane; jj < nq; jj += 32) heavy(warp * ST_DOCS_PER_WARP + q[jj]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                matched += __popc(mj);
+                if ((mj >> lane) & 1u) heavy(warp * ST_DOCS_PER_WARP + j * 32 + lane);
+            }
         }
         __syncthreads();  // every warp is done with this stage: the producer may refill it
     }
 
     // fold the root accumulators (warp shuffle, then one atomic per warp)
-    for (int c = 0; c < p.n_root_counts; c++)
-        if (lane == 0 && matched) atomicAdd((unsigned long long*)p.P->slots[p.root_count_slots[c]].acc, (unsigned long long)matched);
-    uint32_t any = __ballot_sync(0xffffffffu, rseen);
+    if (lane == 0 && matched) {
+        if (p.n_root_counts > 0) atomicAdd((unsigned long long*)p.root_count_acc[0], (unsigned long long)matched);
+        if (p.n_root_counts > 1) atomicAdd((unsigned long long*)p.root_count_acc[1], (unsigned long long)matched);
+    }
+    if (NRG > 0) {
+        uint32_t any = __ballot_sync(0xffffffffu, rseen);
 #pragma unroll
-    for (int g = 0; g < ST_MAXRG; g++) {
-        if (g < p.n_rgroups) {
+        for (int g = 0; g < NRG; g++) {
             const SGroup& G = p.rgroups[g];
             uint64_t s = rsum[g], mn = rmin[g], mx = rmax[g];
 #pragma unroll
@@ -336,22 +362,58 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream(const __grid_constant__ S
             }
             if (lane == 0 && any) {
                 if (G.ops & OPB_SUM) {
-                    const DevSlot& sl = p.P->slots[G.slot_sum];
-                    if (G.kind == TAGG_F64) atomicAdd((double*)sl.acc, __longlong_as_double((long long)s));
-                    else atomicAdd((unsigned long long*)sl.acc, (unsigned long long)s);
-                    sl.seen[0] = 1;
+                    if (G.kind == TAGG_F64) atomicAdd((double*)G.acc_sum, __longlong_as_double((long long)s));
+                    else atomicAdd((unsigned long long*)G.acc_sum, (unsigned long long)s);
+                    *G.seen_sum = 1;
                 }
-                if (G.ops & OPB_MIN) { const DevSlot& sl = p.P->slots[G.slot_min]; atomicMax((unsigned long long*)sl.acc, (unsigned long long)mn); sl.seen[0] = 1; }
-                if (G.ops & OPB_MAX) { const DevSlot& sl = p.P->slots[G.slot_max]; atomicMax((unsigned long long*)sl.acc, (unsigned long long)mx); sl.seen[0] = 1; }
+                if (G.ops & OPB_MIN) { atomicMax((unsigned long long*)G.acc_min, (unsigned long long)mn); *G.seen_min = 1; }
+                if (G.ops & OPB_MAX) { atomicMax((unsigned long long*)G.acc_max, (unsigned long long)mx); *G.seen_max = 1; }
             }
         }
     }
+}
+
+// bucket existence from the bucket counts (when the plan has a count under the bucket node the kernel
+// does not maintain `present` itself: a bucket exists iff its count is non-zero)
+__global__ void k_present_from_counts(const uint64_t* __restrict__ counts, uint8_t* __restrict__ present, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        present[i] = counts[i] != 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
 // host: does the plan have the flat streaming shape?  [filters / post-filters]* -> (root metrics..., one
 // dense TERMS | HISTOGRAM over leaf metrics), every column single-valued.
 // ------------------------------------------------------------------------------------------------------
+typedef void (*stream_fn)(const SParams);
+template <int BUCKET, int NBG, int NRG>
+static stream_fn pick_compact(bool compact) {
+    return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true> : (stream_fn)k_stream<BUCKET, NBG, NRG, false>;
+}
+template <int BUCKET, int NBG>
+static stream_fn pick_nrg(int nrg, bool compact) {
+    switch (nrg) {
+        case 0: return pick_compact<BUCKET, NBG, 0>(compact);
+        case 1: return pick_compact<BUCKET, NBG, 1>(compact);
+        default: return pick_compact<BUCKET, NBG, ST_MAXRG>(compact);
+    }
+}
+template <int BUCKET>
+static stream_fn pick_nbg(int nbg, int nrg, bool compact) {
+    switch (nbg) {
+        case 0: return pick_nrg<BUCKET, 0>(nrg, compact);
+        case 1: return pick_nrg<BUCKET, 1>(nrg, compact);
+        case 2: return pick_nrg<BUCKET, 2>(nrg, compact);
+        default: return pick_nrg<BUCKET, 3>(nrg, compact);
+    }
+}
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact) {
+    switch (bucket) {
+        case BK_NONE: return pick_nrg<BK_NONE, 0>(nrg, compact);
+        case BK_TERMS: return pick_nbg<BK_TERMS>(nbg, nrg, compact);
+        default: return pick_nbg<BK_HIST>(nbg, nrg, compact);
+    }
+}
+
 struct Shape {
     SParams sp;
     std::vector<int> staged;  // DevSegment.cols slot per staged column
@@ -364,7 +426,8 @@ struct Shape {
     }
 };
 
-static bool add_fold(Shape& sh, SGroup* groups, int32_t& n, int maxn, const PlanMeta& m, int node) {
+static bool add_fold(ExecState& es, Shape& sh, SGroup* groups, int& n, int maxn, int node) {
+    const PlanMeta& m = *es.meta;
     const tagg_node& nd = m.nodes[node];
     if (nd.multi) return false;
     int scol = sh.stage_col(m.col_slot[node]);
@@ -382,8 +445,12 @@ static bool add_fold(Shape& sh, SGroup* groups, int32_t& n, int maxn, const Plan
     }
     if (G->ops & bit) return false;  // the same op twice on one column: leave it to the generic kernel
     G->ops |= bit;
-    uint32_t slot = (uint32_t)m.slot_of[node];
-    if (bit == OPB_SUM) G->slot_sum = slot; else if (bit == OPB_MIN) G->slot_min = slot; else G->slot_max = slot;
+    const SlotLayout& SL = es.slots[m.slot_of[node]];
+    uint64_t* acc = (uint64_t*)(es.arena + SL.off_acc);
+    uint8_t* seen = es.arena + SL.off_seen;
+    if (bit == OPB_SUM) { G->acc_sum = acc; G->seen_sum = seen; }
+    else if (bit == OPB_MIN) { G->acc_min = acc; G->seen_min = seen; }
+    else { G->acc_max = acc; G->seen_max = seen; }
     return true;
 }
 
@@ -394,9 +461,10 @@ int stream_try(ExecState& es) {
     SParams& sp = sh.sp;
     memset(&sp, 0, sizeof(sp));
     sp.key_scol = -1;
-    uint32_t n_nodes = (uint32_t)m.nodes.size();
+    const uint32_t n_nodes = (uint32_t)m.nodes.size();
+    const size_t nseg = es.hsegs.size();
 
-    // docsets must have one kind per position across segments (ALL / BITSET mixes are handled per segment)
+    // docset kinds must agree across segments where a column is involved (ALL / BITSET mixes are per segment)
     const DevSegment& S0 = es.hsegs[0];
     for (auto& hs : es.hsegs) {
         if (hs.main.kind == DS_IDS) return 0;  // sparse id lists: the gather (generic) kernel is the right tool
@@ -407,42 +475,49 @@ int stream_try(ExecState& es) {
             if (hs.filters[f].kind == DS_RANGE && hs.filters[f].col != S0.filters[f].col) return 0;
         }
     }
+    // predicate list: pred_src[i] = -2 main docset range, -1 plan node constant, f >= 0 filter docset f
+    std::vector<int> pred_src;
+    auto add_pred = [&](int type, int scol, int src, uint64_t lo, uint64_t hi, const uint8_t* lut) -> bool {
+        if (sp.n_preds >= ST_MAXPRED) return false;
+        int i = sp.n_preds++;
+        sp.pred_type[i] = type;
+        sp.pred_scol[i] = scol;
+        sp.pred_lut[i] = lut;
+        pred_src.push_back(src);
+        (void)lo; (void)hi;
+        return true;
+    };
+    std::vector<std::pair<uint64_t, uint64_t>> pred_const(ST_MAXPRED);
     if (S0.main.kind == DS_RANGE) {
-        SPred& pr = sp.preds[sp.n_preds++];
-        pr.type = PR_MAIN_RANGE;
-        pr.scol = sh.stage_col(S0.main.col);
+        int sc = sh.stage_col(S0.main.col);
+        if (sc < 0 || !add_pred(PR_RANGE, sc, -2, 0, 0, nullptr)) return 0;
     }
     uint32_t node = 0;
     while (node < n_nodes && (m.nodes[node].op == TAGG_OP_FILTER || m.nodes[node].op == TAGG_OP_POST_FILTER)) {
         const tagg_node& nd = m.nodes[node];
-        if (sp.n_preds >= ST_MAXPRED) return 0;
-        SPred& pr = sp.preds[sp.n_preds];
         if (nd.op == TAGG_OP_FILTER) {
-            pr.filter = (int32_t)nd.aux;
             if (S0.filters[nd.aux].kind == DS_RANGE) {
-                pr.type = PR_FILTER_RANGE;
-                pr.scol = sh.stage_col(S0.filters[nd.aux].col);
-                if (pr.scol < 0) return 0;
+                int sc = sh.stage_col(S0.filters[nd.aux].col);
+                if (sc < 0 || !add_pred(PR_RANGE, sc, (int)nd.aux, 0, 0, nullptr)) return 0;
             } else {
-                pr.type = PR_FILTER;
+                if (!add_pred(PR_FILTER, -1, (int)nd.aux, 0, 0, nullptr)) return 0;
             }
         } else {
             if (nd.multi) return 0;
-            pr.type = nd.pred == TAGG_PRED_LUT ? PR_LUT : PR_RANGE;
-            pr.scol = sh.stage_col(m.col_slot[node]);
-            if (pr.scol < 0) return 0;
-            pr.lo = nd.u0;
-            pr.hi = nd.u1;
-            pr.lut = nd.pred == TAGG_PRED_LUT ? es.plan->d_blobs[nd.aux] : nullptr;
+            int sc = sh.stage_col(m.col_slot[node]);
+            if (sc < 0) return 0;
+            if (!add_pred(nd.pred == TAGG_PRED_LUT ? PR_LUT : PR_RANGE, sc, -1, nd.u0, nd.u1,
+                          nd.pred == TAGG_PRED_LUT ? es.plan->d_blobs[nd.aux] : nullptr))
+                return 0;
+            pred_const[sp.n_preds - 1] = {nd.u0, nd.u1};
         }
-        sp.n_preds++;
         node++;
     }
     if (node >= n_nodes) return 0;
-    // FILTER nodes deeper in the tree are not part of the flat shape
-    for (uint32_t i = node; i < n_nodes; i++)
+    for (uint32_t i = node; i < n_nodes; i++)  // narrowing nodes deeper in the tree are not part of the flat shape
         if (m.nodes[i].op == TAGG_OP_FILTER || m.nodes[i].op == TAGG_OP_POST_FILTER) return 0;
 
+    int n_rgroups = 0, n_bgroups = 0, bucket_mode = BK_NONE, bucket_scope = -1;
     std::vector<uint32_t> members;
     if (m.nodes[node].op == TAGG_OP_TUPLE) {
         for (uint32_t c = node + 1; c < m.end[node]; c = m.end[c]) members.push_back(c);
@@ -453,15 +528,15 @@ int stream_try(ExecState& es) {
         const tagg_node& nd = m.nodes[mem];
         if (nd.op == TAGG_OP_COUNT) {
             if (sp.n_root_counts >= 2) return 0;
-            sp.root_count_slots[sp.n_root_counts++] = (uint32_t)m.slot_of[mem];
+            sp.root_count_acc[sp.n_root_counts++] = (uint64_t*)(es.arena + es.slots[m.slot_of[mem]].off_acc);
         } else if (nd.op == TAGG_OP_SUM || nd.op == TAGG_OP_MIN || nd.op == TAGG_OP_MAX) {
-            if (!add_fold(sh, sp.rgroups, sp.n_rgroups, ST_MAXRG, m, (int)mem)) return 0;
+            if (!add_fold(es, sh, sp.rgroups, n_rgroups, ST_MAXRG, (int)mem)) return 0;
         } else if (nd.op == TAGG_OP_TERMS || nd.op == TAGG_OP_HISTOGRAM) {
-            if (sp.bucket_mode != BK_NONE || nd.multi) return 0;
-            int sc = m.own_scope[mem];
-            const ScopeLayout& L = es.scopes[sc];
+            if (bucket_mode != BK_NONE || nd.multi) return 0;
+            bucket_scope = m.own_scope[mem];
+            const ScopeLayout& L = es.scopes[bucket_scope];
             if (L.mode != SCOPE_DENSE) return 0;
-            sp.bucket_mode = nd.op == TAGG_OP_TERMS ? BK_TERMS : BK_HIST;
+            bucket_mode = nd.op == TAGG_OP_TERMS ? BK_TERMS : BK_HIST;
             sp.key_scol = sh.stage_col(m.col_slot[mem]);
             if (sp.key_scol < 0) return 0;
             sp.dom_min = L.dom_min;
@@ -480,9 +555,9 @@ int stream_try(ExecState& es) {
                 const tagg_node& ln = m.nodes[lf];
                 if (ln.op == TAGG_OP_COUNT) {
                     if (sp.n_bcounts >= 2) return 0;
-                    sp.bcount_slots[sp.n_bcounts++] = (uint32_t)m.slot_of[lf];
+                    sp.bcount_acc[sp.n_bcounts++] = (uint64_t*)(es.arena + es.slots[m.slot_of[lf]].off_acc);
                 } else if (ln.op == TAGG_OP_SUM || ln.op == TAGG_OP_MIN || ln.op == TAGG_OP_MAX) {
-                    if (!add_fold(sh, sp.bgroups, sp.n_bgroups, ST_MAXBG, m, (int)lf)) return 0;
+                    if (!add_fold(es, sh, sp.bgroups, n_bgroups, ST_MAXBG, (int)lf)) return 0;
                 } else {
                     return 0;
                 }
@@ -496,7 +571,6 @@ int stream_try(ExecState& es) {
     sp.n_cols = (int32_t)sh.staged.size();
     uint32_t off = 0;
     for (int c = 0; c < sp.n_cols; c++) {
-        sp.col_slot[c] = sh.staged[c];
         uint32_t maxnb = 0;
         for (auto& hs : es.hsegs) maxnb = std::max(maxnb, hs.cols[sh.staged[c]].num_bits);
         sp.soff_col[c] = off;
@@ -506,54 +580,87 @@ int stream_try(ExecState& es) {
     sp.soff_bits = off;
     off += 256 * ST_MAXBITS;
     sp.stage_bytes = (off + 127) & ~127u;
-    size_t smem_bytes = (size_t)ST_STAGES * sp.stage_bytes + ST_WARPS * ST_WORDS_PER_WARP * 32 * 2 + ST_STAGES * 8 + 2 * ST_STAGES * 4 + 64;
+    size_t smem_bytes = (size_t)ST_STAGES * sp.stage_bytes + ST_WARPS * ST_DOCS_PER_WARP * 2 + ST_STAGES * 8 + 2 * ST_STAGES * 4 + 64;
     if (smem_bytes > 200 * 1024) return 0;
 
-    // tile table
-    std::vector<uint32_t> prefix(es.hsegs.size() + 1, 0);
-    for (size_t i = 0; i < es.hsegs.size(); i++) {
-        uint64_t tiles = ((uint64_t)es.hsegs[i].max_doc + ST_TILE - 1) / ST_TILE;
-        uint64_t nx = prefix[i] + tiles;
-        if (nx > 0xffffffffull) return 0;
-        prefix[i + 1] = (uint32_t)nx;
+    // per-segment descriptors
+    std::vector<SegDesc> descs(nseg);
+    uint64_t tiles_total = 0;
+    bool narrowing = sp.n_preds > 0;
+    for (size_t i = 0; i < nseg; i++) {
+        const DevSegment& hs = es.hsegs[i];
+        SegDesc& d = descs[i];
+        memset(&d, 0, sizeof(d));
+        if (tiles_total > 0xffffffffull) return 0;
+        d.tile_begin = (uint32_t)tiles_total;
+        tiles_total += ((uint64_t)hs.max_doc + ST_TILE - 1) / ST_TILE;
+        d.max_doc = hs.max_doc;
+        for (int c = 0; c < sp.n_cols; c++) {
+            const DevColumn& col = hs.cols[sh.staged[c]];
+            d.col_ptr[c] = (const uint8_t*)col.words;
+            d.nb[c] = col.num_bits;
+            d.minv[c] = col.min_value;
+        }
+        if (hs.main.kind == DS_BITSET) { d.flags |= SF_MAIN_BITS; d.bits_ptr[0] = (const uint8_t*)hs.main.words; narrowing = true; }
+        if (hs.has_deletes) { d.flags |= SF_DELETES; d.bits_ptr[1] = (const uint8_t*)hs.deleted; narrowing = true; }
+        for (int pi = 0; pi < sp.n_preds; pi++) {
+            int src = pred_src[pi];
+            if (src == -2) { d.pred_lo[pi] = hs.main.lo; d.pred_hi[pi] = hs.main.hi; }
+            else if (src == -1) { d.pred_lo[pi] = pred_const[pi].first; d.pred_hi[pi] = pred_const[pi].second; }
+            else {
+                const DevDocset& fd = hs.filters[src];
+                if (sp.pred_type[pi] == PR_RANGE) { d.pred_lo[pi] = fd.lo; d.pred_hi[pi] = fd.hi; }
+                else if (fd.kind == DS_BITSET) { d.flags |= SF_PRED_BITS0 << pi; d.bits_ptr[2 + pi] = (const uint8_t*)fd.words; }
+                else if (fd.kind != DS_ALL) d.flags |= SF_PRED_NONE0 << pi;
+            }
+        }
     }
-    sp.n_segs = (uint32_t)es.hsegs.size();
-    sp.n_tiles = prefix.back();
-    // the bucket slots' Option flags coincide with bucket existence in the flat shape: alias them
-    if (sp.bucket_mode != BK_NONE) {
-        int sc = -1;
-        for (size_t s = 1; s < es.scopes.size(); s++) sc = (int)s;
+    if (tiles_total > 0xffffffffull) return 0;
+    sp.n_segs = (uint32_t)nseg;
+    sp.n_tiles = (uint32_t)tiles_total;
+
+    // Option flags of the bucket slots coincide with bucket existence in the flat shape: alias them
+    if (bucket_mode != BK_NONE) {
         for (size_t k = 0; k < es.slots.size(); k++)
-            if (m.scope_of[m.slot_node[k]] == sc) es.slots[k].off_seen = es.scopes[sc].off_present;
+            if (m.scope_of[m.slot_node[k]] == bucket_scope) es.slots[k].off_seen = es.scopes[bucket_scope].off_present;
     }
     es.path_used = 2;
     if (sp.n_tiles == 0) return 1;
-    uint32_t* d_prefix = nullptr;
-    if (cudaMallocAsync((void**)&d_prefix, prefix.size() * 4, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "tile table allocation failed");
-    es.temps.push_back(d_prefix);
-    if (cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
-        return -tagg_fail(TAGG_ERR_CUDA, "tile table upload failed");
-    sp.tile_prefix = d_prefix;
-    sp.segs = es.d_segs;
-    sp.P = es.d_plan;
-    // compaction pays when most documents are filtered out; with no narrowing it is pure overhead
-    bool narrowing = sp.n_preds > 0;
-    for (auto& hs : es.hsegs) narrowing = narrowing || hs.main.kind == DS_BITSET || hs.has_deletes;
-    sp.compact = narrowing ? 1 : 0;
+    SegDesc* d_descs = nullptr;
+    if (cudaMallocAsync((void**)&d_descs, nseg * sizeof(SegDesc), es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "segment table allocation failed");
+    es.temps.push_back(d_descs);
+    if (cudaMemcpyAsync(d_descs, descs.data(), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, es.st) != cudaSuccess)
+        return -tagg_fail(TAGG_ERR_CUDA, "segment table upload failed");
+    sp.segs = d_descs;
+    uint8_t* present = sp.present;
+    if (bucket_mode != BK_NONE && sp.n_bcounts > 0) sp.present = nullptr;  // derived from the counts below
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return -tagg_fail(TAGG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
-        attr_set = true;
+    // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
+    int nrg_t = n_rgroups <= 1 ? n_rgroups : ST_MAXRG;
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing);
+    static std::mutex attr_mu;
+    static std::vector<stream_fn> attr_done;
+    {
+        std::lock_guard<std::mutex> g(attr_mu);
+        if (std::find(attr_done.begin(), attr_done.end(), fn) == attr_done.end()) {
+            if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+                return -tagg_fail(TAGG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+            attr_done.push_back(fn);
+        }
     }
     int per_sm = (int)std::min<size_t>(2048 / ST_THREADS, (227 * 1024) / (smem_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, sp.n_tiles);
-    k_stream<<<grid, ST_THREADS, smem_bytes, es.st>>>(sp);
+    fn<<<grid, ST_THREADS, smem_bytes, es.st>>>(sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
     es.ctx->launches++;
     es.n_launches++;
+    if (bucket_mode != BK_NONE && sp.n_bcounts > 0) {
+        uint64_t n = es.scopes[bucket_scope].capacity;
+        k_present_from_counts<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, es.st>>>(sp.bcount_acc[0], present, n);
+        es.ctx->launches++;
+        es.n_launches++;
+    }
     return 1;
 }
