@@ -29,12 +29,13 @@
 
 #include "exec.h"
 
-#define ST_THREADS 256
-#define ST_WARPS (ST_THREADS / 32)
+#define ST_WARPS 8                                   // consumer warps per group
+#define ST_GROUP_THREADS ((ST_WARPS + 1) * 32)       // + 1 producer warp
+#define ST_MAXGROUPS 3
 #define ST_TILE TAGG_TILE_DOCS
 #define ST_WORDS_PER_WARP (ST_TILE / 32 / ST_WARPS)  // 8
 #define ST_DOCS_PER_WARP (ST_WORDS_PER_WARP * 32)    // 256
-#define ST_STAGES 3
+#define ST_MAXSTAGES 4
 #define ST_MAXCOLS 6
 #define ST_MAXPRED 4
 #define ST_MAXBITS (2 + ST_MAXPRED)
@@ -48,7 +49,7 @@ enum { SF_MAIN_BITS = 1, SF_DELETES = 2, SF_PRED_BITS0 = 4 /* << i */, SF_PRED_N
 
 // Everything the kernel needs to know about one segment, prepared on the host.
 struct SegDesc {
-    uint32_t tile_begin, max_doc, flags, pad;
+    uint32_t tile_begin, max_doc, flags, tile_bytes;  // tile_bytes: bytes one staged tile of this segment moves
     const uint8_t* col_ptr[ST_MAXCOLS];
     uint64_t minv[ST_MAXCOLS];
     uint32_t nb[ST_MAXCOLS];
@@ -70,6 +71,10 @@ struct SParams {
     uint32_t soff_col[ST_MAXCOLS];  // byte offset of each staged column inside a stage
     uint32_t soff_bits;             // bitset slots (256 B each) inside a stage
     uint32_t stage_bytes;
+    uint32_t n_stages, group_bytes, table_bytes;   // shared-memory layout
+    uint32_t soff_tab_count[2];                    // STAB: CTA-private bucket count tables (u32)
+    uint32_t soff_tab_sum[ST_MAXBG];               // STAB: CTA-private bucket sum tables (u64 / f64)
+    uint32_t soff_tab_min[ST_MAXBG], soff_tab_max[ST_MAXBG];  // STAB: CTA-private min / max tables (u64, max-form)
     int32_t n_preds;
     int32_t pred_type[ST_MAXPRED];
     int32_t pred_scol[ST_MAXPRED];
@@ -115,259 +120,442 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-// A staged column of the current tile, held in registers.
-struct TCol {
-    const uint32_t* s32;
-    uint64_t minv, mask;
-    uint32_t nb;
+// What the producer warp tells the consumers about a staged tile.
+struct TileDesc {
+    uint32_t n_valid, flags;
+    uint32_t nb[ST_MAXCOLS];
+    uint64_t minv[ST_MAXCOLS];
+    uint64_t pred_lo[ST_MAXPRED], pred_hi[ST_MAXPRED];
 };
-__device__ __forceinline__ TCol tcol(const SParams& p, const SegDesc* S, const uint8_t* stage, int scol) {
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// A staged column of the current tile, held in registers (32-bit shared-memory address, split masks).
+struct TCol {
+    uint32_t saddr, nb, mlo, mhi, minlo, minhi;
+};
+// TileDesc fields are read with explicit shared-memory loads (a generic-pointer load is tracked on the
+// long scoreboard and costs a global-memory-class latency)
+#define TD_N_VALID 0
+#define TD_FLAGS 4
+#define TD_NB(c) (8 + 4 * (c))
+#define TD_MINV(c) (8 + 4 * ST_MAXCOLS + 8 * (c))
+#define TD_PRED_LO(i) (8 + 12 * ST_MAXCOLS + 8 * (i))
+#define TD_PRED_HI(i) (8 + 12 * ST_MAXCOLS + 8 * ST_MAXPRED + 8 * (i))
+static_assert(sizeof(TileDesc) == 8 + 12 * ST_MAXCOLS + 16 * ST_MAXPRED, "TileDesc layout");
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ TCol tcol(const SParams& p, uint32_t T, uint32_t stage_saddr, int scol) {
     TCol c;
-    c.s32 = (const uint32_t*)(stage + p.soff_col[scol]);
-    c.nb = S->nb[scol];
-    c.minv = S->minv[scol];
-    c.mask = c.nb == 64 ? ~0ull : ((1ull << c.nb) - 1ull);
+    c.saddr = stage_saddr + p.soff_col[scol];
+    c.nb = lds32(T + TD_NB(scol));
+    uint64_t mn = lds64(T + TD_MINV(scol));
+    c.minlo = (uint32_t)mn;
+    c.minhi = (uint32_t)(mn >> 32);
+    c.mlo = c.nb >= 32 ? 0xffffffffu : ((1u << c.nb) - 1u);
+    c.mhi = c.nb <= 32 ? 0u : (c.nb >= 64 ? 0xffffffffu : ((1u << (c.nb - 32)) - 1u));
     return c;
 }
-// value i of a staged column tile (tantivy BitUnpacker::get on shared memory, 32-bit aligned loads) -> code
-__device__ __forceinline__ uint64_t tget(const TCol& c, uint32_t i) {
+// packed delta of value i (tantivy BitUnpacker::get on shared memory, 32-bit aligned loads)
+__device__ __forceinline__ void tdelta(const TCol& c, uint32_t i, uint32_t& lo, uint32_t& hi) {
     uint32_t bit = i * c.nb;
-    uint32_t wi = bit >> 5, sh = bit & 31u;
-    uint32_t w0 = c.s32[wi], w1 = c.s32[wi + 1];
-    uint32_t lo = __funnelshift_r(w0, w1, sh);
-    uint32_t hi = 0;
+    uint32_t a = c.saddr + ((bit >> 5) << 2), sh = bit & 31u;
+    uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+    lo = __funnelshift_r(w0, w1, sh) & c.mlo;
+    hi = 0;
     if (c.nb > 32) {
-        uint32_t w2 = c.s32[wi + 2];
-        hi = __funnelshift_r(w1, w2, sh);
+        uint32_t w2 = lds32(a + 8);
+        hi = __funnelshift_r(w1, w2, sh) & c.mhi;
     }
-    return ((((uint64_t)hi << 32) | lo) & c.mask) + c.minv;
+}
+__device__ __forceinline__ uint64_t tget(const TCol& c, uint32_t i) {  // -> code
+    uint32_t lo, hi;
+    tdelta(c, i, lo, hi);
+    return (((uint64_t)hi << 32) | lo) + (((uint64_t)c.minhi << 32) | c.minlo);
 }
 
-template <int BUCKET, int NBG, int NRG, bool COMPACT>
-__global__ void __launch_bounds__(ST_THREADS) k_stream(const __grid_constant__ SParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stages = smem;
-    uint16_t* queues = (uint16_t*)(smem + (size_t)ST_STAGES * p.stage_bytes);
-    uint64_t* full = (uint64_t*)(queues + ST_WARPS * ST_DOCS_PER_WARP);
-    uint32_t* stage_seg = (uint32_t*)(full + ST_STAGES);  // [stage] = segment, [ST_STAGES + stage] = local tile
+#define ST_U 4  // matched documents handled together per lane: independent chains hide table latency
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    if (tid == 0) {
-        for (int s = 0; s < ST_STAGES; s++) mbar_init(full + s, 1);
+// Warp-specialised: a CTA is G groups of 9 warps — warp 0 of a group is the TMA producer, warps 1..8
+// consume.  Stages are handed over with mbarriers only (full: TMA bytes landed; empty: 8 consumer
+// warps released the stage), so consumer warps never synchronise with one another inside the loop.
+// STAB: bucket counts (u32) and bucket sums live in a shared-memory table private to the CTA and are
+// merged into the global table once at the end (global atomics on a few thousand hot addresses
+// serialise in L2; shared-memory atomics do not — tools/atom_bench.cu).
+template <int BUCKET, int NBG, int NRG, bool COMPACT, bool STAB>
+__global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(const __grid_constant__ SParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n_groups = blockDim.x / ST_GROUP_THREADS;
+    const uint32_t group = tid / ST_GROUP_THREADS;
+    const uint32_t gwarp = (tid % ST_GROUP_THREADS) >> 5;  // 0 = producer, 1..8 = consumers
+    const uint32_t S = p.n_stages;
+
+    // shared layout: [tables][per group: stages | queues | tile descs | barriers]
+    uint8_t* gbase = smem + p.table_bytes + (size_t)group * p.group_bytes;
+    uint8_t* stages = gbase;
+    uint16_t* queues = (uint16_t*)(gbase + (size_t)S * p.stage_bytes);
+    TileDesc* tdesc = (TileDesc*)(queues + ST_WARPS * ST_DOCS_PER_WARP);
+    uint64_t* full = (uint64_t*)(tdesc + S);
+    uint64_t* empty = full + S;
+
+    if (tid % ST_GROUP_THREADS == 0) {
+        for (uint32_t s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, ST_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (STAB) {
+        uint32_t* t32 = (uint32_t*)smem;
+        for (uint32_t i = tid; i < p.table_bytes / 4; i += blockDim.x) t32[i] = 0;
     }
     __syncthreads();
 
-    // thread 0 is the producer: tiles are visited in ascending order, so the segment cursor only advances
-    uint32_t cur_seg = 0;
-    auto issue = [&](uint32_t tile, int stage) {
-        while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= tile) cur_seg++;
-        const SegDesc* S = p.segs + cur_seg;
-        uint32_t lt = tile - S->tile_begin;
-        stage_seg[stage] = cur_seg;
-        stage_seg[ST_STAGES + stage] = lt;
-        uint8_t* base = stages + (size_t)stage * p.stage_bytes;
-        uint32_t flags = S->flags;
-        uint32_t bytes = 0;
-        for (int c = 0; c < p.n_cols; c++) bytes += (ST_TILE / 8) * S->nb[c];
-        bytes += (ST_TILE / 8) * __popc(flags & 0xffu);
-        if (bytes == 0) {  // nothing to stage (count over AllQuery): complete the phase by hand
-            mbar_arrive(full + stage);
-            return;
-        }
-        mbar_expect_tx(full + stage, bytes);
-        for (int c = 0; c < p.n_cols; c++) {
-            uint32_t cb = (ST_TILE / 8) * S->nb[c];
-            if (cb) tma_bulk_g2s(base + p.soff_col[c], S->col_ptr[c] + (size_t)lt * cb, cb, full + stage);
-        }
-        uint8_t* bits = base + p.soff_bits;
-        for (int b = 0; b < ST_MAXBITS; b++)
-            if (flags & (1u << b)) tma_bulk_g2s(bits + 256 * b, S->bits_ptr[b] + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
-    };
+    const uint64_t first = (uint64_t)blockIdx.x * n_groups + group, step = (uint64_t)gridDim.x * n_groups;
 
-    // per-thread root accumulators
-    uint64_t rsum[NRG ? NRG : 1], rmin[NRG ? NRG : 1], rmax[NRG ? NRG : 1];
-    bool rseen = false;
-#pragma unroll
-    for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
-    uint32_t matched = 0;  // every lane holds the warp's count
-
-    uint32_t my_first = blockIdx.x, step = gridDim.x;
-    if (tid == 0) {
-        for (int s = 0; s < ST_STAGES - 1; s++) {
-            uint64_t t = (uint64_t)my_first + (uint64_t)s * step;
-            if (t < p.n_tiles) issue((uint32_t)t, s);
-        }
-    }
-    uint32_t k = 0;
-    for (uint64_t tile = my_first; tile < p.n_tiles; tile += step, k++) {
-        const int stage = k % ST_STAGES;
-        const uint32_t parity = (k / ST_STAGES) & 1u;
-        if (tid == 0) {
-            uint64_t nt = tile + (uint64_t)(ST_STAGES - 1) * step;
-            if (nt < p.n_tiles) issue((uint32_t)nt, (k + ST_STAGES - 1) % ST_STAGES);
-        }
-        mbar_wait(full + stage, parity);
-
-        const uint8_t* sbase = stages + (size_t)stage * p.stage_bytes;
-        const SegDesc* S = p.segs + stage_seg[stage];
-        const uint32_t lt = stage_seg[ST_STAGES + stage];
-        const uint32_t flags = S->flags;
-        const uint32_t* bits = (const uint32_t*)(sbase + p.soff_bits);
-        // documents of this tile that exist
-        const uint64_t tile_doc0 = (uint64_t)lt * ST_TILE;
-        const uint32_t n_valid = (uint32_t)min((uint64_t)ST_TILE, (uint64_t)S->max_doc - tile_doc0);
-
-        // ---- phase 1: one match-mask word per lane (lanes 0..7) ------------------------------------
-        uint32_t m = 0;
-        if (lane < ST_WORDS_PER_WARP) {
-            uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
-            uint32_t d0 = wi * 32;
-            m = d0 + 32 <= n_valid ? 0xffffffffu : (d0 >= n_valid ? 0u : ((1u << (n_valid - d0)) - 1u));
-            if (flags & SF_MAIN_BITS) m &= bits[wi];
-            if (flags & SF_DELETES) m &= ~bits[64 + wi];  // searcher.rs:41-46
-            for (int i = 0; i < p.n_preds; i++) {
-                if (flags & (SF_PRED_BITS0 << i)) m &= bits[128 + 64 * i + wi];
-                if (flags & (SF_PRED_NONE0 << i)) m = 0;
+    if (gwarp == 0) {
+        // ======================= producer warp =======================
+        // A single thread preparing a tile is a ~1000-cycle serial chain, which caps a group at one tile
+        // per microsecond.  The work is spread over the lanes instead: lane c issues the TMA copy of
+        // staged column c, lane 8+b that of bitset b, lanes 16.. publish the tile descriptor, lane 0 arms
+        // the barrier.  (A copy may complete before the barrier is armed: the phase cannot flip while the
+        // producer's own arrival is pending.)
+        uint32_t cur_seg = 0, k = 0;
+        for (uint64_t tile = first; tile < p.n_tiles; tile += step, k++) {
+            const uint32_t stage = k % S;
+            if (k >= S) mbar_wait(empty + stage, ((k / S) - 1) & 1u);
+            while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= tile) cur_seg++;
+            const SegDesc* Sg = p.segs + cur_seg;
+            const uint32_t lt = (uint32_t)tile - Sg->tile_begin;
+            const uint32_t flags = Sg->flags;
+            TileDesc* T = tdesc + stage;
+            uint8_t* base = stages + (size_t)stage * p.stage_bytes;
+            if (lane < (uint32_t)p.n_cols) {
+                uint32_t cb = (ST_TILE / 8) * Sg->nb[lane];
+                if (cb) tma_bulk_g2s(base + p.soff_col[lane], Sg->col_ptr[lane] + (size_t)lt * cb, cb, full + stage);
+            } else if (lane >= 8 && lane < 8 + ST_MAXBITS) {
+                uint32_t b = lane - 8;
+                if (flags & (1u << b)) tma_bulk_g2s(base + p.soff_bits + 256 * b, Sg->bits_ptr[b] + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
+            } else if (lane == 16) {
+                T->n_valid = (uint32_t)min((uint64_t)ST_TILE, (uint64_t)Sg->max_doc - (uint64_t)lt * ST_TILE);
+                T->flags = flags;
+            } else if (lane >= 17 && lane < 17 + ST_MAXCOLS) {
+                uint32_t c = lane - 17;
+                if (c < (uint32_t)p.n_cols) { T->nb[c] = Sg->nb[c]; T->minv[c] = Sg->minv[c]; }
+            } else if (lane >= 24 && lane < 24 + ST_MAXPRED) {
+                uint32_t i = lane - 24;
+                if (i < (uint32_t)p.n_preds) { T->pred_lo[i] = Sg->pred_lo[i]; T->pred_hi[i] = Sg->pred_hi[i]; }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t bytes = Sg->tile_bytes;
+                if (bytes) mbar_expect_tx(full + stage, bytes);
+                else mbar_arrive(full + stage);  // nothing to stage (count over AllQuery)
             }
         }
-        // value predicates: evaluated per document, folded in with ballots
-        for (int i = 0; i < p.n_preds; i++) {
-            const int type = p.pred_type[i];
-            if (type == PR_FILTER) continue;
-            const TCol pc = tcol(p, S, sbase, p.pred_scol[i]);
-            const uint64_t lo = S->pred_lo[i], hi = S->pred_hi[i];
-            const uint8_t* lut = p.pred_lut[i];
+    } else {
+        // ======================= consumer warps =======================
+        const uint32_t warp = gwarp - 1;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        const uint32_t q_saddr = smem_u32(queues + warp * ST_DOCS_PER_WARP);
+        const uint32_t stages_saddr = smem_u32(stages);
+        const uint32_t tdesc_saddr = smem_u32(tdesc);
+        uint32_t* const scount0 = (uint32_t*)(smem + p.soff_tab_count[0]);
+        uint32_t* const scount1 = (uint32_t*)(smem + p.soff_tab_count[1]);
+        const uint32_t ops_b0 = NBG > 0 ? p.bgroups[0].ops : 0, ops_b1 = NBG > 1 ? p.bgroups[1].ops : 0, ops_b2 = NBG > 2 ? p.bgroups[2].ops : 0;
+        const uint32_t dom_size32 = (uint32_t)p.dom_size;
+
+        // per-thread root accumulators
+        uint64_t rsum[NRG ? NRG : 1], rmin[NRG ? NRG : 1], rmax[NRG ? NRG : 1];
+        bool rseen = false;
 #pragma unroll
-            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-                if (mj) {
-                    uint64_t code = tget(pc, warp * ST_DOCS_PER_WARP + j * 32 + lane);
-                    bool ok;
-                    if (type == PR_LUT) {
-                        uint64_t r = code - lo;
-                        ok = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
-                    } else {
-                        ok = code >= lo && code <= hi;
-                    }
-                    mj &= __ballot_sync(0xffffffffu, ok);
-                    if (lane == j) m = mj;
+        for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
+        uint32_t matched = 0;  // every lane holds the warp's count
+
+        uint32_t k = 0;
+        for (uint64_t tile = first; tile < p.n_tiles; tile += step, k++) {
+            const uint32_t stage = k % S;
+            mbar_wait(full + stage, (k / S) & 1u);
+            const uint32_t stage_saddr = stages_saddr + stage * p.stage_bytes;
+            const uint32_t T = tdesc_saddr + stage * (uint32_t)sizeof(TileDesc);
+            const uint32_t flags = lds32(T + TD_FLAGS), n_valid = lds32(T + TD_N_VALID);
+            const uint32_t bits_saddr = stage_saddr + p.soff_bits;
+
+            // ---- phase 1: one match-mask word per lane (lanes 0..7) --------------------------------
+            uint32_t m = 0;
+            if (lane < ST_WORDS_PER_WARP) {
+                uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
+                uint32_t d0 = wi * 32;
+                m = d0 + 32 <= n_valid ? 0xffffffffu : (d0 >= n_valid ? 0u : ((1u << (n_valid - d0)) - 1u));
+                if (flags & SF_MAIN_BITS) m &= lds32(bits_saddr + wi * 4);
+                if (flags & SF_DELETES) m &= ~lds32(bits_saddr + 256 + wi * 4);  // searcher.rs:41-46
+                for (int i = 0; i < p.n_preds; i++) {
+                    if (flags & (SF_PRED_BITS0 << i)) m &= lds32(bits_saddr + 512 + 256 * i + wi * 4);
+                    if (flags & (SF_PRED_NONE0 << i)) m = 0;
                 }
             }
+            // value predicates: evaluated per document, folded in with ballots
+            for (int i = 0; i < p.n_preds; i++) {
+                const int type = p.pred_type[i];
+                if (type == PR_FILTER) continue;
+                const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
+                const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
+                const uint8_t* lut = p.pred_lut[i];
+#pragma unroll
+                for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                    uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                    if (mj) {
+                        uint64_t code = tget(pc, warp * ST_DOCS_PER_WARP + j * 32 + lane);
+                        bool ok;
+                        if (type == PR_LUT) {
+                            uint64_t r = code - lo;
+                            ok = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
+                        } else {
+                            ok = code >= lo && code <= hi;
+                        }
+                        mj &= __ballot_sync(0xffffffffu, ok);
+                        if (lane == j) m = mj;
+                    }
+                }
+            }
+
+            // per-tile column descriptors of the roles this instantiation has, in registers
+            TCol kc, bc[NBG ? NBG : 1], rc[NRG ? NRG : 1];
+            uint32_t krel = 0;  // TERMS: (column min - domain min); keys are dense and < 2^24 wide
+            if (BUCKET != BK_NONE) {
+                kc = tcol(p, T, stage_saddr, p.key_scol);
+                krel = (uint32_t)(lds64(T + TD_MINV(p.key_scol)) - p.dom_min);
+            }
+#pragma unroll
+            for (int g = 0; g < NBG; g++) bc[g] = tcol(p, T, stage_saddr, p.bgroups[g].scol);
+#pragma unroll
+            for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
+
+            // ST_U matched documents per lane at a time; `act[u]` says whether slot u holds a document
+            auto heavy = [&](const uint32_t (&dl)[ST_U], const bool (&act_in)[ST_U]) {
+                bool act[ST_U];
+#pragma unroll
+                for (int u = 0; u < ST_U; u++) { act[u] = act_in[u]; rseen = rseen || act[u]; }
+#pragma unroll
+                for (int g = 0; g < NRG; g++) {
+                    const SGroup& G = p.rgroups[g];
+                    if (G.ops) {
+#pragma unroll
+                        for (int u = 0; u < ST_U; u++) {
+                            if (act[u]) {
+                                uint64_t code = tget(rc[g], dl[u]);
+                                if (G.ops & OPB_SUM) {
+                                    if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
+                                    else rsum[g] += code_to_bits(G.kind, code);
+                                }
+                                if (G.ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
+                                if (G.ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
+                            }
+                        }
+                    }
+                }
+                if (BUCKET != BK_NONE) {
+                    uint32_t rel[ST_U];
+#pragma unroll
+                    for (int u = 0; u < ST_U; u++) {
+                        rel[u] = 0;
+                        if (act[u]) {
+                            if (BUCKET == BK_TERMS) {
+                                uint32_t lo, hi;
+                                tdelta(kc, dl[u], lo, hi);
+                                rel[u] = lo + krel;
+                                act[u] = rel[u] < dom_size32;
+                            } else {
+                                uint64_t ord;
+                                // NaN or below start: skipped (histogram.rs:138-145)
+                                if (hist_ord(tget(kc, dl[u]), p.f0, p.f1, &ord) && ord >= p.dom_min && ord - p.dom_min < p.dom_size) rel[u] = (uint32_t)(ord - p.dom_min);
+                                else act[u] = false;
+                            }
+                        }
+                    }
+                    // min / max cells: read all ST_U of them first (independent chains overlap the latency).
+                    // STAB: the cell is in the CTA's shared table.  Otherwise it is global: a plain (L1-cached,
+                    // possibly stale) read filters most documents; survivors are confirmed at L2 below.
+                    uint64_t cur_min[NBG ? NBG : 1][ST_U], cur_max[NBG ? NBG : 1][ST_U];
+#pragma unroll
+                    for (int g = 0; g < NBG; g++) {
+                        const uint32_t ops = g == 0 ? ops_b0 : g == 1 ? ops_b1 : ops_b2;
+                        const uint64_t* tmin = STAB ? (const uint64_t*)(smem + p.soff_tab_min[g]) : p.bgroups[g].acc_min;
+                        const uint64_t* tmax = STAB ? (const uint64_t*)(smem + p.soff_tab_max[g]) : p.bgroups[g].acc_max;
+#pragma unroll
+                        for (int u = 0; u < ST_U; u++) {
+                            cur_min[g][u] = ~0ull; cur_max[g][u] = ~0ull;
+                            if (act[u] && (ops & OPB_MIN)) cur_min[g][u] = tmin[rel[u]];
+                            if (act[u] && (ops & OPB_MAX)) cur_max[g][u] = tmax[rel[u]];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < ST_U; u++) {
+                        if (act[u]) {
+                            if (STAB) {
+                                if (p.n_bcounts > 0) atomicAdd(scount0 + rel[u], 1u);
+                                if (p.n_bcounts > 1) atomicAdd(scount1 + rel[u], 1u);
+                            } else {
+                                if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel[u]), 1ull);
+                                if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel[u]), 1ull);
+                            }
+                            if (p.present && !p.present[rel[u]]) p.present[rel[u]] = 1;  // only when no count names the bucket
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < NBG; g++) {
+                        const SGroup& G = p.bgroups[g];
+                        const uint32_t ops = g == 0 ? ops_b0 : g == 1 ? ops_b1 : ops_b2;
+#pragma unroll
+                        for (int u = 0; u < ST_U; u++) {
+                            if (act[u]) {
+                                uint64_t code = tget(bc[g], dl[u]);
+                                if (ops & OPB_SUM) {
+                                    uint64_t* a = STAB ? (uint64_t*)(smem + p.soff_tab_sum[g]) + rel[u] : G.acc_sum + rel[u];
+                                    if (G.kind == TAGG_F64) atomicAdd((double*)a, code_to_f64(code));
+                                    else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code));
+                                }
+                                if ((ops & OPB_MIN) && cur_min[g][u] < ~code) {
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_min[g]) + rel[u], (unsigned long long)~code);
+                                    else if (__ldcg(G.acc_min + rel[u]) < ~code) atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code);
+                                }
+                                if ((ops & OPB_MAX) && cur_max[g][u] < code) {
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_max[g]) + rel[u], (unsigned long long)code);
+                                    else if (__ldcg(G.acc_max + rel[u]) < code) atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code);
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+
+            if (COMPACT) {
+                // ---- phase 2: compact the set bits of the 8 words into the warp's queue ----------------
+                uint32_t incl = __popc(m);
+#pragma unroll
+                for (int o = 1; o < ST_WORDS_PER_WARP; o <<= 1) {
+                    uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (uint32_t)o) incl += up;
+                }
+                const uint32_t excl = incl - __popc(m);
+                const uint32_t nq = __shfl_sync(0xffffffffu, incl, ST_WORDS_PER_WARP - 1);
+#pragma unroll
+                for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                    uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                    uint32_t oj = __shfl_sync(0xffffffffu, excl, j);
+                    if ((mj >> lane) & 1u) {
+                        uint32_t at = q_saddr + 2 * (oj + __popc(mj & lt_mask));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(at), "h"((uint16_t)(warp * ST_DOCS_PER_WARP + j * 32 + lane)) : "memory");
+                    }
+                }
+                matched += nq;
+                __syncwarp();
+                // ---- phase 3: full warps drain the queue, ST_U documents per lane -----------------------
+                for (uint32_t j0 = 0; j0 < nq; j0 += 32 * ST_U) {
+                    uint32_t dl[ST_U];
+                    bool act[ST_U];
+#pragma unroll
+                    for (int u = 0; u < ST_U; u++) {
+                        uint32_t jj = j0 + u * 32 + lane;
+                        act[u] = jj < nq;
+                        uint16_t d = 0;
+                        if (act[u]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(q_saddr + 2 * jj));
+                        dl[u] = d;
+                    }
+                    heavy(dl, act);
+                }
+            } else {
+#pragma unroll
+                for (int j0 = 0; j0 < ST_WORDS_PER_WARP; j0 += ST_U) {
+                    uint32_t dl[ST_U];
+                    bool act[ST_U];
+#pragma unroll
+                    for (int u = 0; u < ST_U; u++) {
+                        uint32_t mj = __shfl_sync(0xffffffffu, m, j0 + u);
+                        matched += __popc(mj);
+                        act[u] = (mj >> lane) & 1u;
+                        dl[u] = warp * ST_DOCS_PER_WARP + (j0 + u) * 32 + lane;
+                    }
+                    heavy(dl, act);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);  // this warp is done with the stage
         }
 
-        // per-tile column descriptors of the roles this instantiation has, in registers
-        TCol kc, bc[NBG ? NBG : 1], rc[NRG ? NRG : 1];
-        if (BUCKET != BK_NONE) kc = tcol(p, S, sbase, p.key_scol);
-#pragma unroll
-        for (int g = 0; g < NBG; g++) bc[g] = tcol(p, S, sbase, p.bgroups[g].scol);
-#pragma unroll
-        for (int g = 0; g < NRG; g++) rc[g] = tcol(p, S, sbase, p.rgroups[g].scol);
-
-        auto heavy = [&](uint32_t dl) {
-            rseen = true;
+        // fold the root accumulators (warp shuffle, then one atomic per warp)
+        if (lane == 0 && matched) {
+            if (p.n_root_counts > 0) atomicAdd((unsigned long long*)p.root_count_acc[0], (unsigned long long)matched);
+            if (p.n_root_counts > 1) atomicAdd((unsigned long long*)p.root_count_acc[1], (unsigned long long)matched);
+        }
+        if (NRG > 0) {
+            uint32_t any = __ballot_sync(0xffffffffu, rseen);
 #pragma unroll
             for (int g = 0; g < NRG; g++) {
                 const SGroup& G = p.rgroups[g];
-                if (G.ops) {
-                    uint64_t code = tget(rc[g], dl);
+                uint64_t s = rsum[g], mn = rmin[g], mx = rmax[g];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    uint64_t s2 = __shfl_xor_sync(0xffffffffu, s, o), mn2 = __shfl_xor_sync(0xffffffffu, mn, o), mx2 = __shfl_xor_sync(0xffffffffu, mx, o);
+                    if (G.kind == TAGG_F64) s = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)s), __longlong_as_double((long long)s2)));
+                    else s += s2;
+                    mn = mn2 > mn ? mn2 : mn;
+                    mx = mx2 > mx ? mx2 : mx;
+                }
+                if (lane == 0 && any) {
                     if (G.ops & OPB_SUM) {
-                        if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
-                        else rsum[g] += code_to_bits(G.kind, code);
+                        if (G.kind == TAGG_F64) atomicAdd((double*)G.acc_sum, __longlong_as_double((long long)s));
+                        else atomicAdd((unsigned long long*)G.acc_sum, (unsigned long long)s);
+                        *G.seen_sum = 1;
                     }
-                    if (G.ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
-                    if (G.ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
+                    if (G.ops & OPB_MIN) { atomicMax((unsigned long long*)G.acc_min, (unsigned long long)mn); *G.seen_min = 1; }
+                    if (G.ops & OPB_MAX) { atomicMax((unsigned long long*)G.acc_max, (unsigned long long)mx); *G.seen_max = 1; }
                 }
-            }
-            if (BUCKET != BK_NONE) {
-                uint64_t key = tget(kc, dl);
-                if (BUCKET == BK_HIST) {
-                    if (!hist_ord(key, p.f0, p.f1, &key)) return;  // NaN or below start: skipped (histogram.rs:138-145)
-                }
-                uint64_t rel = key - p.dom_min;
-                if (key < p.dom_min || rel >= p.dom_size) return;
-                if (p.present && !p.present[rel]) p.present[rel] = 1;
-                if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel), 1ull);
-                if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel), 1ull);
-#pragma unroll
-                for (int g = 0; g < NBG; g++) {
-                    const SGroup& G = p.bgroups[g];
-                    uint64_t code = tget(bc[g], dl);
-                    if (G.ops & OPB_SUM) {
-                        if (G.kind == TAGG_F64) atomicAdd((double*)(G.acc_sum + rel), code_to_f64(code));
-                        else atomicAdd((unsigned long long*)(G.acc_sum + rel), (unsigned long long)code_to_bits(G.kind, code));
-                    }
-                    if (G.ops & OPB_MIN) {
-                        uint64_t v = ~code;
-                        if (G.acc_min[rel] < v) atomicMax((unsigned long long*)(G.acc_min + rel), (unsigned long long)v);
-                    }
-                    if (G.ops & OPB_MAX) {
-                        if (G.acc_max[rel] < code) atomicMax((unsigned long long*)(G.acc_max + rel), (unsigned long long)code);
-                    }
-                }
-            }
-        };
-
-        if (COMPACT) {
-            // ---- phase 2: compact the set bits of the 8 words into the warp's queue ------------------
-            uint32_t incl = __popc(m);
-#pragma unroll
-            for (int o = 1; o < ST_WORDS_PER_WARP; o <<= 1) {
-                uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= (uint32_t)o) incl += up;
-            }
-            const uint32_t excl = incl - __popc(m);
-            const uint32_t nq = __shfl_sync(0xffffffffu, incl, ST_WORDS_PER_WARP - 1);
-            uint16_t* q = queues + warp * ST_DOCS_PER_WARP;
-#pragma unroll
-            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-                uint32_t oj = __shfl_sync(0xffffffffu, excl, j);
-                if ((mj >> lane) & 1u) q[oj + __popc(mj & lt_mask)] = (uint16_t)(j * 32 + lane);
-            }
-            matched += nq;
-            __syncwarp();
-            // ---- phase 3: full warps drain the queue --------------------------------------------------
-            for (uint32_t jj = lane; jj < nq; jj += 32) heavy(warp * ST_DOCS_PER_WARP + q[jj]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-                uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-                matched += __popc(mj);
-                if ((mj >> lane) & 1u) heavy(warp * ST_DOCS_PER_WARP + j * 32 + lane);
             }
         }
-        __syncthreads();  // every warp is done with this stage: the producer may refill it
     }
 
-    // fold the root accumulators (warp shuffle, then one atomic per warp)
-    if (lane == 0 && matched) {
-        if (p.n_root_counts > 0) atomicAdd((unsigned long long*)p.root_count_acc[0], (unsigned long long)matched);
-        if (p.n_root_counts > 1) atomicAdd((unsigned long long*)p.root_count_acc[1], (unsigned long long)matched);
-    }
-    if (NRG > 0) {
-        uint32_t any = __ballot_sync(0xffffffffu, rseen);
-#pragma unroll
-        for (int g = 0; g < NRG; g++) {
-            const SGroup& G = p.rgroups[g];
-            uint64_t s = rsum[g], mn = rmin[g], mx = rmax[g];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                uint64_t s2 = __shfl_xor_sync(0xffffffffu, s, o), mn2 = __shfl_xor_sync(0xffffffffu, mn, o), mx2 = __shfl_xor_sync(0xffffffffu, mx, o);
-                if (G.kind == TAGG_F64) s = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)s), __longlong_as_double((long long)s2)));
-                else s += s2;
-                mn = mn2 > mn ? mn2 : mn;
-                mx = mx2 > mx ? mx2 : mx;
+    if (STAB) {
+        // merge the CTA's private table into the global one
+        __syncthreads();
+        for (int c = 0; c < p.n_bcounts; c++) {
+            const uint32_t* sc = (const uint32_t*)(smem + p.soff_tab_count[c]);
+            for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
+                uint32_t v = sc[i];
+                if (v) atomicAdd((unsigned long long*)(p.bcount_acc[c] + i), (unsigned long long)v);
             }
-            if (lane == 0 && any) {
-                if (G.ops & OPB_SUM) {
-                    if (G.kind == TAGG_F64) atomicAdd((double*)G.acc_sum, __longlong_as_double((long long)s));
-                    else atomicAdd((unsigned long long*)G.acc_sum, (unsigned long long)s);
-                    *G.seen_sum = 1;
+        }
+#pragma unroll
+        for (int g = 0; g < NBG; g++) {
+            const SGroup& G = p.bgroups[g];
+            if (G.ops & OPB_SUM) {
+                const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_sum[g]);
+                for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
+                    uint64_t v = ss[i];
+                    if (v) {
+                        if (G.kind == TAGG_F64) atomicAdd((double*)(G.acc_sum + i), __longlong_as_double((long long)v));
+                        else atomicAdd((unsigned long long*)(G.acc_sum + i), (unsigned long long)v);
+                    }
                 }
-                if (G.ops & OPB_MIN) { atomicMax((unsigned long long*)G.acc_min, (unsigned long long)mn); *G.seen_min = 1; }
-                if (G.ops & OPB_MAX) { atomicMax((unsigned long long*)G.acc_max, (unsigned long long)mx); *G.seen_max = 1; }
+            }
+            if (G.ops & OPB_MIN) {
+                const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_min[g]);
+                for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
+                    uint64_t v = ss[i];
+                    if (v && __ldcg(G.acc_min + i) < v) atomicMax((unsigned long long*)(G.acc_min + i), (unsigned long long)v);
+                }
+            }
+            if (G.ops & OPB_MAX) {
+                const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_max[g]);
+                for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
+                    uint64_t v = ss[i];
+                    if (v && __ldcg(G.acc_max + i) < v) atomicMax((unsigned long long*)(G.acc_max + i), (unsigned long long)v);
+                }
             }
         }
     }
@@ -386,31 +574,33 @@ __global__ void k_present_from_counts(const uint64_t* __restrict__ counts, uint8
 // ------------------------------------------------------------------------------------------------------
 typedef void (*stream_fn)(const SParams);
 template <int BUCKET, int NBG, int NRG>
-static stream_fn pick_compact(bool compact) {
-    return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true> : (stream_fn)k_stream<BUCKET, NBG, NRG, false>;
+static stream_fn pick_flags(bool compact, bool stab) {
+    if (BUCKET == BK_NONE) stab = false;
+    if (stab) return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true, (BUCKET != BK_NONE)> : (stream_fn)k_stream<BUCKET, NBG, NRG, false, (BUCKET != BK_NONE)>;
+    return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true, false> : (stream_fn)k_stream<BUCKET, NBG, NRG, false, false>;
 }
 template <int BUCKET, int NBG>
-static stream_fn pick_nrg(int nrg, bool compact) {
+static stream_fn pick_nrg(int nrg, bool compact, bool stab) {
     switch (nrg) {
-        case 0: return pick_compact<BUCKET, NBG, 0>(compact);
-        case 1: return pick_compact<BUCKET, NBG, 1>(compact);
-        default: return pick_compact<BUCKET, NBG, ST_MAXRG>(compact);
+        case 0: return pick_flags<BUCKET, NBG, 0>(compact, stab);
+        case 1: return pick_flags<BUCKET, NBG, 1>(compact, stab);
+        default: return pick_flags<BUCKET, NBG, ST_MAXRG>(compact, stab);
     }
 }
 template <int BUCKET>
-static stream_fn pick_nbg(int nbg, int nrg, bool compact) {
+static stream_fn pick_nbg(int nbg, int nrg, bool compact, bool stab) {
     switch (nbg) {
-        case 0: return pick_nrg<BUCKET, 0>(nrg, compact);
-        case 1: return pick_nrg<BUCKET, 1>(nrg, compact);
-        case 2: return pick_nrg<BUCKET, 2>(nrg, compact);
-        default: return pick_nrg<BUCKET, 3>(nrg, compact);
+        case 0: return pick_nrg<BUCKET, 0>(nrg, compact, stab);
+        case 1: return pick_nrg<BUCKET, 1>(nrg, compact, stab);
+        case 2: return pick_nrg<BUCKET, 2>(nrg, compact, stab);
+        default: return pick_nrg<BUCKET, 3>(nrg, compact, stab);
     }
 }
-static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact) {
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab) {
     switch (bucket) {
-        case BK_NONE: return pick_nrg<BK_NONE, 0>(nrg, compact);
-        case BK_TERMS: return pick_nbg<BK_TERMS>(nbg, nrg, compact);
-        default: return pick_nbg<BK_HIST>(nbg, nrg, compact);
+        case BK_NONE: return pick_nrg<BK_NONE, 0>(nrg, compact, false);
+        case BK_TERMS: return pick_nbg<BK_TERMS>(nbg, nrg, compact, stab);
+        default: return pick_nbg<BK_HIST>(nbg, nrg, compact, stab);
     }
 }
 
@@ -580,8 +770,6 @@ int stream_try(ExecState& es) {
     sp.soff_bits = off;
     off += 256 * ST_MAXBITS;
     sp.stage_bytes = (off + 127) & ~127u;
-    size_t smem_bytes = (size_t)ST_STAGES * sp.stage_bytes + ST_WARPS * ST_DOCS_PER_WARP * 2 + ST_STAGES * 8 + 2 * ST_STAGES * 4 + 64;
-    if (smem_bytes > 200 * 1024) return 0;
 
     // per-segment descriptors
     std::vector<SegDesc> descs(nseg);
@@ -615,6 +803,10 @@ int stream_try(ExecState& es) {
             }
         }
     }
+    for (auto& d : descs) {
+        d.tile_bytes = (ST_TILE / 8) * __builtin_popcount(d.flags & 0xffu);
+        for (int c = 0; c < sp.n_cols; c++) d.tile_bytes += (ST_TILE / 8) * d.nb[c];
+    }
     if (tiles_total > 0xffffffffull) return 0;
     sp.n_segs = (uint32_t)nseg;
     sp.n_tiles = (uint32_t)tiles_total;
@@ -632,26 +824,66 @@ int stream_try(ExecState& es) {
     if (cudaMemcpyAsync(d_descs, descs.data(), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, es.st) != cudaSuccess)
         return -tagg_fail(TAGG_ERR_CUDA, "segment table upload failed");
     sp.segs = d_descs;
+
+    // shared-memory plan.  STAB (CTA-private count / sum tables) whenever the tables leave room for the
+    // staging ring; then one CTA per SM with as many groups and stages as fit.
+    const size_t SMEM_MAX = 225 * 1024;
+    auto group_bytes = [&](uint32_t stages) {
+        size_t b = (size_t)stages * sp.stage_bytes + ST_WARPS * ST_DOCS_PER_WARP * 2 + (size_t)stages * sizeof(TileDesc) + 2 * stages * 8;
+        return (b + 127) & ~(size_t)127;
+    };
+    size_t table_bytes = 0;
+    bool stab = false;
+    if (bucket_mode != BK_NONE) {
+        size_t tb = 0;
+        for (int c = 0; c < sp.n_bcounts; c++) { sp.soff_tab_count[c] = (uint32_t)tb; tb += ((sp.dom_size * 4 + 127) & ~127ull); }
+        for (int g = 0; g < n_bgroups; g++) {
+            if (sp.bgroups[g].ops & OPB_SUM) { sp.soff_tab_sum[g] = (uint32_t)tb; tb += ((sp.dom_size * 8 + 127) & ~127ull); }
+            if (sp.bgroups[g].ops & OPB_MIN) { sp.soff_tab_min[g] = (uint32_t)tb; tb += ((sp.dom_size * 8 + 127) & ~127ull); }
+            if (sp.bgroups[g].ops & OPB_MAX) { sp.soff_tab_max[g] = (uint32_t)tb; tb += ((sp.dom_size * 8 + 127) & ~127ull); }
+        }
+        if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
+    }
+    uint32_t n_groups = 1, n_stages = 3;
+    if (stab) {
+        const uint32_t cand[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
+        bool ok = false;
+        for (auto& c : cand)
+            if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
+        if (!ok) { stab = false; table_bytes = 0; }
+    }
+    if (!stab) {
+        n_groups = 1;
+        n_stages = group_bytes(3) <= SMEM_MAX ? 3 : 2;
+        if (group_bytes(n_stages) > SMEM_MAX) return 0;
+    }
+    sp.n_stages = n_stages;
+    sp.group_bytes = (uint32_t)group_bytes(n_stages);
+    sp.table_bytes = (uint32_t)table_bytes;
+    size_t smem_bytes = table_bytes + (size_t)n_groups * sp.group_bytes;
     uint8_t* present = sp.present;
     if (bucket_mode != BK_NONE && sp.n_bcounts > 0) sp.present = nullptr;  // derived from the counts below
 
     // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
     int nrg_t = n_rgroups <= 1 ? n_rgroups : ST_MAXRG;
-    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing);
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab);
     static std::mutex attr_mu;
     static std::vector<stream_fn> attr_done;
     {
         std::lock_guard<std::mutex> g(attr_mu);
         if (std::find(attr_done.begin(), attr_done.end(), fn) == attr_done.end()) {
-            if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX) != cudaSuccess)
                 return -tagg_fail(TAGG_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
             attr_done.push_back(fn);
         }
     }
-    int per_sm = (int)std::min<size_t>(2048 / ST_THREADS, (227 * 1024) / (smem_bytes + 1024));
-    if (per_sm < 1) per_sm = 1;
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, sp.n_tiles);
-    fn<<<grid, ST_THREADS, smem_bytes, es.st>>>(sp);
+    int threads = (int)n_groups * ST_GROUP_THREADS;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, threads, smem_bytes) != cudaSuccess || per_sm < 1)
+        return -tagg_fail(TAGG_ERR_CUDA, "k_stream does not fit an SM (%zu bytes of shared memory)", smem_bytes);
+    uint64_t work_units = ((uint64_t)sp.n_tiles + n_groups - 1) / n_groups;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, work_units);
+    fn<<<grid, threads, smem_bytes, es.st>>>(sp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
     es.ctx->launches++;
