@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "exec.h"
 
@@ -75,7 +76,7 @@ struct SParams {
     uint32_t soff_tab_count[2];                    // STAB: CTA-private bucket count tables (u32)
     uint32_t soff_tab_sum[ST_MAXBG];               // STAB: CTA-private bucket sum tables (u64 / f64)
     uint32_t soff_tab_min[ST_MAXBG], soff_tab_max[ST_MAXBG];  // STAB: CTA-private min / max tables (u64, max-form)
-    int32_t n_preds;
+    int32_t n_preds, n_vpreds;                     // all predicates / those evaluated on column values
     int32_t pred_type[ST_MAXPRED];
     int32_t pred_scol[ST_MAXPRED];
     const uint8_t* pred_lut[ST_MAXPRED];
@@ -85,7 +86,8 @@ struct SParams {
     int32_t key_scol;
     uint64_t dom_min, dom_size;
     double f0, f1;
-    uint8_t* present;  // nullptr: derived from the bucket counts after the kernel
+    uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
+    uint8_t* present_out;  // STAB: written by the final table merge
     int32_t n_bcounts;
     uint64_t* bcount_acc[2];
     SGroup bgroups[ST_MAXBG];
@@ -111,6 +113,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_saddr), "r"(parity)
             : "memory");
     } while (!done);
 }
@@ -181,16 +198,27 @@ __device__ __forceinline__ uint64_t tget(const TCol& c, uint32_t i) {  // -> cod
     return (((uint64_t)hi << 32) | lo) + (((uint64_t)c.minhi << 32) | c.minlo);
 }
 
-#define ST_U 4  // matched documents handled together per lane: independent chains hide table latency
+// Kernel shape.  RT shapes read the per-group op masks from the launch parameters (any flat plan);
+// CT shapes bake the op masks of the single bucket / root column group into the instantiation, so the
+// compiler drops every path the plan does not have (the hot configurations use these).
+template <int BUCKET_, int NBG_, int NRG_, bool COMPACT_, bool STAB_, int BOPS_ = -1, int ROPS_ = -1>
+struct Shp {
+    static constexpr int BUCKET = BUCKET_, NBG = NBG_, NRG = NRG_;
+    static constexpr bool COMPACT = COMPACT_, STAB = STAB_;
+    static constexpr int BOPS = BOPS_, ROPS = ROPS_;
+};
 
 // Warp-specialised: a CTA is G groups of 9 warps — warp 0 of a group is the TMA producer, warps 1..8
 // consume.  Stages are handed over with mbarriers only (full: TMA bytes landed; empty: 8 consumer
 // warps released the stage), so consumer warps never synchronise with one another inside the loop.
-// STAB: bucket counts (u32) and bucket sums live in a shared-memory table private to the CTA and are
-// merged into the global table once at the end (global atomics on a few thousand hot addresses
-// serialise in L2; shared-memory atomics do not — tools/atom_bench.cu).
-template <int BUCKET, int NBG, int NRG, bool COMPACT, bool STAB>
+// STAB: the bucket tables (counts u32; sums / min / max u64) live in shared memory, private to the CTA,
+// and are merged into the global tables once at the end (global atomics on a few thousand hot addresses
+// serialise in L2 and L2 reads of them cap near 130 G/s; shared-memory atomics do not —
+// tools/atom_bench.cu).
+template <class SH>
 __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(const __grid_constant__ SParams p) {
+    constexpr int BUCKET = SH::BUCKET, NBG = SH::NBG, NRG = SH::NRG;
+    constexpr bool COMPACT = SH::COMPACT, STAB = SH::STAB;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t n_groups = blockDim.x / ST_GROUP_THREADS;
@@ -225,10 +253,10 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         // staged column c, lane 8+b that of bitset b, lanes 16.. publish the tile descriptor, lane 0 arms
         // the barrier.  (A copy may complete before the barrier is armed: the phase cannot flip while the
         // producer's own arrival is pending.)
-        uint32_t cur_seg = 0, k = 0;
-        for (uint64_t tile = first; tile < p.n_tiles; tile += step, k++) {
-            const uint32_t stage = k % S;
-            if (k >= S) mbar_wait(empty + stage, ((k / S) - 1) & 1u);
+        uint32_t cur_seg = 0, stage = 0, parity = 1;  // parity of the empty-barrier phase to wait for (first lap: none)
+        bool first_lap = true;
+        for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
+            if (!first_lap) mbar_wait(empty + stage, parity);
             while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= tile) cur_seg++;
             const SegDesc* Sg = p.segs + cur_seg;
             const uint32_t lt = (uint32_t)tile - Sg->tile_begin;
@@ -257,17 +285,20 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 if (bytes) mbar_expect_tx(full + stage, bytes);
                 else mbar_arrive(full + stage);  // nothing to stage (count over AllQuery)
             }
+            if (++stage == S) { stage = 0; parity ^= 1u; first_lap = false; }
         }
     } else {
         // ======================= consumer warps =======================
         const uint32_t warp = gwarp - 1;
-        const uint32_t lt_mask = (1u << lane) - 1u;
+        const uint32_t lane_bit = 1u << lane, lt_mask = lane_bit - 1u;
         const uint32_t q_saddr = smem_u32(queues + warp * ST_DOCS_PER_WARP);
         const uint32_t stages_saddr = smem_u32(stages);
         const uint32_t tdesc_saddr = smem_u32(tdesc);
-        uint32_t* const scount0 = (uint32_t*)(smem + p.soff_tab_count[0]);
-        uint32_t* const scount1 = (uint32_t*)(smem + p.soff_tab_count[1]);
-        const uint32_t ops_b0 = NBG > 0 ? p.bgroups[0].ops : 0, ops_b1 = NBG > 1 ? p.bgroups[1].ops : 0, ops_b2 = NBG > 2 ? p.bgroups[2].ops : 0;
+        const uint32_t smem_saddr = smem_u32(smem);
+        // op masks: compile-time for CT shapes (single group), launch parameters otherwise
+        const uint32_t ops_b0 = SH::BOPS >= 0 ? (uint32_t)SH::BOPS : (NBG > 0 ? p.bgroups[0].ops : 0u);
+        const uint32_t ops_b1 = NBG > 1 ? p.bgroups[1].ops : 0u, ops_b2 = NBG > 2 ? p.bgroups[2].ops : 0u;
+        const uint32_t ops_r0 = SH::ROPS >= 0 ? (uint32_t)SH::ROPS : (NRG > 0 ? p.rgroups[0].ops : 0u);
         const uint32_t dom_size32 = (uint32_t)p.dom_size;
 
         // per-thread root accumulators
@@ -277,10 +308,10 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
         uint32_t matched = 0;  // every lane holds the warp's count
 
-        uint32_t k = 0;
-        for (uint64_t tile = first; tile < p.n_tiles; tile += step, k++) {
-            const uint32_t stage = k % S;
-            mbar_wait(full + stage, (k / S) & 1u);
+        const uint32_t full_saddr = smem_u32(full), empty_saddr = smem_u32(empty);
+        uint32_t stage = 0, parity = 0;
+        for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
+            mbar_wait_s(full_saddr + 8 * stage, parity);
             const uint32_t stage_saddr = stages_saddr + stage * p.stage_bytes;
             const uint32_t T = tdesc_saddr + stage * (uint32_t)sizeof(TileDesc);
             const uint32_t flags = lds32(T + TD_FLAGS), n_valid = lds32(T + TD_N_VALID);
@@ -289,37 +320,41 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             // ---- phase 1: one match-mask word per lane (lanes 0..7) --------------------------------
             uint32_t m = 0;
             if (lane < ST_WORDS_PER_WARP) {
-                uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
-                uint32_t d0 = wi * 32;
+                const uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
+                const uint32_t d0 = wi * 32;
+                const uint32_t wa = bits_saddr + wi * 4;
                 m = d0 + 32 <= n_valid ? 0xffffffffu : (d0 >= n_valid ? 0u : ((1u << (n_valid - d0)) - 1u));
-                if (flags & SF_MAIN_BITS) m &= lds32(bits_saddr + wi * 4);
-                if (flags & SF_DELETES) m &= ~lds32(bits_saddr + 256 + wi * 4);  // searcher.rs:41-46
-                for (int i = 0; i < p.n_preds; i++) {
-                    if (flags & (SF_PRED_BITS0 << i)) m &= lds32(bits_saddr + 512 + 256 * i + wi * 4);
-                    if (flags & (SF_PRED_NONE0 << i)) m = 0;
-                }
+                if (flags & SF_MAIN_BITS) m &= lds32(wa);
+                if (flags & SF_DELETES) m &= ~lds32(wa + 256);  // searcher.rs:41-46
+                if (flags & (SF_PRED_BITS0 << 0)) m &= lds32(wa + 512);
+                if (flags & (SF_PRED_BITS0 << 1)) m &= lds32(wa + 768);
+                if (flags & (SF_PRED_BITS0 << 2)) m &= lds32(wa + 1024);
+                if (flags & (SF_PRED_BITS0 << 3)) m &= lds32(wa + 1280);
+                if (flags & (SF_PRED_NONE0 * 15u)) m = 0;  // a filter query that matches nothing in this segment
             }
-            // value predicates: evaluated per document, folded in with ballots
-            for (int i = 0; i < p.n_preds; i++) {
-                const int type = p.pred_type[i];
-                if (type == PR_FILTER) continue;
-                const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
-                const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
-                const uint8_t* lut = p.pred_lut[i];
+            // value predicates (post_filter / COLUMN_RANGE docsets): per document, folded in with ballots
+            if (p.n_vpreds) {
+                for (int i = 0; i < p.n_preds; i++) {
+                    const int type = p.pred_type[i];
+                    if (type == PR_FILTER) continue;
+                    const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
+                    const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
+                    const uint8_t* lut = p.pred_lut[i];
 #pragma unroll
-                for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-                    uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-                    if (mj) {
-                        uint64_t code = tget(pc, warp * ST_DOCS_PER_WARP + j * 32 + lane);
-                        bool ok;
-                        if (type == PR_LUT) {
-                            uint64_t r = code - lo;
-                            ok = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
-                        } else {
-                            ok = code >= lo && code <= hi;
+                    for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                        uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                        if (mj) {
+                            uint64_t code = tget(pc, warp * ST_DOCS_PER_WARP + j * 32 + lane);
+                            bool ok;
+                            if (type == PR_LUT) {
+                                uint64_t r = code - lo;
+                                ok = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
+                            } else {
+                                ok = code >= lo && code <= hi;
+                            }
+                            mj &= __ballot_sync(0xffffffffu, ok);
+                            if (lane == j) m = mj;
                         }
-                        mj &= __ballot_sync(0xffffffffu, ok);
-                        if (lane == j) m = mj;
                     }
                 }
             }
@@ -336,33 +371,37 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
             for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
 
-            // ST_U matched documents per lane at a time; `act[u]` says whether slot u holds a document
-            auto heavy = [&](const uint32_t (&dl)[ST_U], const bool (&act_in)[ST_U]) {
-                bool act[ST_U];
+            // U matched documents per lane at a time (independent chains overlap the table latency).
+            // CHECK: slots may be empty (act[u] false) — the ragged tail; otherwise every slot is live.
+            auto process = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
+                constexpr int U = decltype(U_)::value;
+                constexpr bool CHECK = decltype(CHECK_)::value;
+                bool act[U];
 #pragma unroll
-                for (int u = 0; u < ST_U; u++) { act[u] = act_in[u]; rseen = rseen || act[u]; }
+                for (int u = 0; u < U; u++) { act[u] = CHECK ? act_in[u] : true; rseen = rseen || act[u]; }
 #pragma unroll
                 for (int g = 0; g < NRG; g++) {
                     const SGroup& G = p.rgroups[g];
-                    if (G.ops) {
+                    const uint32_t ops = g == 0 ? ops_r0 : G.ops;
+                    if (ops) {
 #pragma unroll
-                        for (int u = 0; u < ST_U; u++) {
+                        for (int u = 0; u < U; u++) {
                             if (act[u]) {
                                 uint64_t code = tget(rc[g], dl[u]);
-                                if (G.ops & OPB_SUM) {
+                                if (ops & OPB_SUM) {
                                     if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
                                     else rsum[g] += code_to_bits(G.kind, code);
                                 }
-                                if (G.ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
-                                if (G.ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
+                                if (ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
+                                if (ops & OPB_MAX) rmax[g] = code > rmax[g] ? code : rmax[g];
                             }
                         }
                     }
                 }
                 if (BUCKET != BK_NONE) {
-                    uint32_t rel[ST_U];
+                    uint32_t rel[U];
 #pragma unroll
-                    for (int u = 0; u < ST_U; u++) {
+                    for (int u = 0; u < U; u++) {
                         rel[u] = 0;
                         if (act[u]) {
                             if (BUCKET == BK_TERMS) {
@@ -378,114 +417,124 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             }
                         }
                     }
-                    // min / max cells: read all ST_U of them first (independent chains overlap the latency).
-                    // STAB: the cell is in the CTA's shared table.  Otherwise it is global: a plain (L1-cached,
-                    // possibly stale) read filters most documents; survivors are confirmed at L2 below.
-                    uint64_t cur_min[NBG ? NBG : 1][ST_U], cur_max[NBG ? NBG : 1][ST_U];
+                    // bucket counts (STAB: also the bucket-existence record)
 #pragma unroll
-                    for (int g = 0; g < NBG; g++) {
-                        const uint32_t ops = g == 0 ? ops_b0 : g == 1 ? ops_b1 : ops_b2;
-                        const uint64_t* tmin = STAB ? (const uint64_t*)(smem + p.soff_tab_min[g]) : p.bgroups[g].acc_min;
-                        const uint64_t* tmax = STAB ? (const uint64_t*)(smem + p.soff_tab_max[g]) : p.bgroups[g].acc_max;
-#pragma unroll
-                        for (int u = 0; u < ST_U; u++) {
-                            cur_min[g][u] = ~0ull; cur_max[g][u] = ~0ull;
-                            if (act[u] && (ops & OPB_MIN)) cur_min[g][u] = tmin[rel[u]];
-                            if (act[u] && (ops & OPB_MAX)) cur_max[g][u] = tmax[rel[u]];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < ST_U; u++) {
+                    for (int u = 0; u < U; u++) {
                         if (act[u]) {
                             if (STAB) {
-                                if (p.n_bcounts > 0) atomicAdd(scount0 + rel[u], 1u);
-                                if (p.n_bcounts > 1) atomicAdd(scount1 + rel[u], 1u);
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_tab_count[0] + 4 * rel[u]) : "memory");
+                                if (p.n_bcounts > 1) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_tab_count[1] + 4 * rel[u]) : "memory");
                             } else {
                                 if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel[u]), 1ull);
                                 if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel[u]), 1ull);
+                                if (p.present && !p.present[rel[u]]) p.present[rel[u]] = 1;  // only when no count names the bucket
                             }
-                            if (p.present && !p.present[rel[u]]) p.present[rel[u]] = 1;  // only when no count names the bucket
                         }
                     }
 #pragma unroll
                     for (int g = 0; g < NBG; g++) {
                         const SGroup& G = p.bgroups[g];
                         const uint32_t ops = g == 0 ? ops_b0 : g == 1 ? ops_b1 : ops_b2;
+                        uint64_t code[U], cur_min[U], cur_max[U];
+                        // min / max cells: read all U of them first.  STAB: the CTA's shared table.  Otherwise
+                        // global: a plain (L1, possibly stale) read filters most documents, survivors are
+                        // confirmed at L2 before the atomic.
 #pragma unroll
-                        for (int u = 0; u < ST_U; u++) {
+                        for (int u = 0; u < U; u++) {
+                            code[u] = 0; cur_min[u] = ~0ull; cur_max[u] = ~0ull;
                             if (act[u]) {
-                                uint64_t code = tget(bc[g], dl[u]);
+                                code[u] = tget(bc[g], dl[u]);
+                                if (ops & OPB_MIN) cur_min[u] = STAB ? lds64(smem_saddr + p.soff_tab_min[g] + 8 * rel[u]) : G.acc_min[rel[u]];
+                                if (ops & OPB_MAX) cur_max[u] = STAB ? lds64(smem_saddr + p.soff_tab_max[g] + 8 * rel[u]) : G.acc_max[rel[u]];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            if (act[u]) {
                                 if (ops & OPB_SUM) {
                                     uint64_t* a = STAB ? (uint64_t*)(smem + p.soff_tab_sum[g]) + rel[u] : G.acc_sum + rel[u];
-                                    if (G.kind == TAGG_F64) atomicAdd((double*)a, code_to_f64(code));
-                                    else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code));
+                                    if (G.kind == TAGG_F64) atomicAdd((double*)a, code_to_f64(code[u]));
+                                    else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code[u]));
                                 }
-                                if ((ops & OPB_MIN) && cur_min[g][u] < ~code) {
-                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_min[g]) + rel[u], (unsigned long long)~code);
-                                    else if (__ldcg(G.acc_min + rel[u]) < ~code) atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code);
+                                if ((ops & OPB_MIN) && cur_min[u] < ~code[u]) {
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_min[g]) + rel[u], (unsigned long long)~code[u]);
+                                    else if (__ldcg(G.acc_min + rel[u]) < ~code[u]) atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
                                 }
-                                if ((ops & OPB_MAX) && cur_max[g][u] < code) {
-                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_max[g]) + rel[u], (unsigned long long)code);
-                                    else if (__ldcg(G.acc_max + rel[u]) < code) atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code);
+                                if ((ops & OPB_MAX) && cur_max[u] < code[u]) {
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_max[g]) + rel[u], (unsigned long long)code[u]);
+                                    else if (__ldcg(G.acc_max + rel[u]) < code[u]) atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
                                 }
                             }
                         }
                     }
                 }
             };
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            using I4 = std::integral_constant<int, 4>;
 
             if (COMPACT) {
                 // ---- phase 2: compact the set bits of the 8 words into the warp's queue ----------------
-                uint32_t incl = __popc(m);
-#pragma unroll
-                for (int o = 1; o < ST_WORDS_PER_WARP; o <<= 1) {
-                    uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= (uint32_t)o) incl += up;
-                }
-                const uint32_t excl = incl - __popc(m);
-                const uint32_t nq = __shfl_sync(0xffffffffu, incl, ST_WORDS_PER_WARP - 1);
+                uint32_t nq = 0;
 #pragma unroll
                 for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
-                    uint32_t mj = __shfl_sync(0xffffffffu, m, j);
-                    uint32_t oj = __shfl_sync(0xffffffffu, excl, j);
-                    if ((mj >> lane) & 1u) {
-                        uint32_t at = q_saddr + 2 * (oj + __popc(mj & lt_mask));
+                    const uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                    if (mj & lane_bit) {
+                        const uint32_t at = q_saddr + 2 * (nq + __popc(mj & lt_mask));
                         asm volatile("st.shared.u16 [%0], %1;" ::"r"(at), "h"((uint16_t)(warp * ST_DOCS_PER_WARP + j * 32 + lane)) : "memory");
                     }
+                    nq += __popc(mj);
                 }
                 matched += nq;
                 __syncwarp();
-                // ---- phase 3: full warps drain the queue, ST_U documents per lane -----------------------
-                for (uint32_t j0 = 0; j0 < nq; j0 += 32 * ST_U) {
-                    uint32_t dl[ST_U];
-                    bool act[ST_U];
-#pragma unroll
-                    for (int u = 0; u < ST_U; u++) {
-                        uint32_t jj = j0 + u * 32 + lane;
-                        act[u] = jj < nq;
-                        uint16_t d = 0;
-                        if (act[u]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d) : "r"(q_saddr + 2 * jj));
-                        dl[u] = d;
-                    }
-                    heavy(dl, act);
+                // ---- phase 3: full warps drain the queue: branch-free batches of 64, then the ragged tail --
+                uint32_t j0 = 0;
+                for (; j0 + 64 <= nq; j0 += 64) {
+                    uint32_t dl[2];
+                    uint16_t d0, d1;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d1) : "r"(q_saddr + 2 * (j0 + 32 + lane)));
+                    dl[0] = d0; dl[1] = d1;
+                    process(I2{}, std::false_type{}, dl, nullptr);
+                }
+                for (; j0 < nq; j0 += 32) {
+                    uint32_t dl[1];
+                    bool act[1];
+                    act[0] = j0 + lane < nq;
+                    uint16_t d0 = 0;
+                    if (act[0]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
+                    dl[0] = d0;
+                    process(I1{}, std::true_type{}, dl, act);
                 }
             } else {
+                // nothing narrows the doc stream: every document of the tile is matched (ragged only in a
+                // segment's last tile)
+                const uint32_t wbase = warp * ST_DOCS_PER_WARP;
+                if (n_valid == ST_TILE) {
+                    matched += ST_DOCS_PER_WARP;
 #pragma unroll
-                for (int j0 = 0; j0 < ST_WORDS_PER_WARP; j0 += ST_U) {
-                    uint32_t dl[ST_U];
-                    bool act[ST_U];
+                    for (int j0 = 0; j0 < ST_WORDS_PER_WARP; j0 += 4) {
+                        uint32_t dl[4];
 #pragma unroll
-                    for (int u = 0; u < ST_U; u++) {
-                        uint32_t mj = __shfl_sync(0xffffffffu, m, j0 + u);
-                        matched += __popc(mj);
-                        act[u] = (mj >> lane) & 1u;
-                        dl[u] = warp * ST_DOCS_PER_WARP + (j0 + u) * 32 + lane;
+                        for (int u = 0; u < 4; u++) dl[u] = wbase + (j0 + u) * 32 + lane;
+                        process(I4{}, std::false_type{}, dl, nullptr);
                     }
-                    heavy(dl, act);
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
+                        uint32_t mj = __shfl_sync(0xffffffffu, m, j);
+                        matched += __popc(mj);
+                        uint32_t dl[1];
+                        bool act[1];
+                        dl[0] = wbase + j * 32 + lane;
+                        act[0] = (mj >> lane) & 1u;
+                        process(I1{}, std::true_type{}, dl, act);
+                    }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);  // this warp is done with the stage
+            if (lane == 0) mbar_arrive_s(empty_saddr + 8 * stage);  // this warp is done with the stage
+            if (++stage == S) { stage = 0; parity ^= 1u; }
         }
 
         // fold the root accumulators (warp shuffle, then one atomic per warp)
@@ -498,6 +547,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
             for (int g = 0; g < NRG; g++) {
                 const SGroup& G = p.rgroups[g];
+                const uint32_t ops = g == 0 ? ops_r0 : G.ops;
                 uint64_t s = rsum[g], mn = rmin[g], mx = rmax[g];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -508,32 +558,42 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     mx = mx2 > mx ? mx2 : mx;
                 }
                 if (lane == 0 && any) {
-                    if (G.ops & OPB_SUM) {
+                    if (ops & OPB_SUM) {
                         if (G.kind == TAGG_F64) atomicAdd((double*)G.acc_sum, __longlong_as_double((long long)s));
                         else atomicAdd((unsigned long long*)G.acc_sum, (unsigned long long)s);
                         *G.seen_sum = 1;
                     }
-                    if (G.ops & OPB_MIN) { atomicMax((unsigned long long*)G.acc_min, (unsigned long long)mn); *G.seen_min = 1; }
-                    if (G.ops & OPB_MAX) { atomicMax((unsigned long long*)G.acc_max, (unsigned long long)mx); *G.seen_max = 1; }
+                    if (ops & OPB_MIN) { atomicMax((unsigned long long*)G.acc_min, (unsigned long long)mn); *G.seen_min = 1; }
+                    if (ops & OPB_MAX) { atomicMax((unsigned long long*)G.acc_max, (unsigned long long)mx); *G.seen_max = 1; }
                 }
             }
         }
     }
 
     if (STAB) {
-        // merge the CTA's private table into the global one
+        // merge the CTA's private tables into the global ones; count table 0 always exists in STAB mode
+        // (hidden when the plan has no count) and is the record of which buckets exist
         __syncthreads();
-        for (int c = 0; c < p.n_bcounts; c++) {
-            const uint32_t* sc = (const uint32_t*)(smem + p.soff_tab_count[c]);
+        const uint32_t* sc0 = (const uint32_t*)(smem + p.soff_tab_count[0]);
+        for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
+            uint32_t v = sc0[i];
+            if (v) {
+                if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + i), (unsigned long long)v);
+                if (!p.present_out[i]) p.present_out[i] = 1;
+            }
+        }
+        if (p.n_bcounts > 1) {
+            const uint32_t* sc = (const uint32_t*)(smem + p.soff_tab_count[1]);
             for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
                 uint32_t v = sc[i];
-                if (v) atomicAdd((unsigned long long*)(p.bcount_acc[c] + i), (unsigned long long)v);
+                if (v) atomicAdd((unsigned long long*)(p.bcount_acc[1] + i), (unsigned long long)v);
             }
         }
 #pragma unroll
         for (int g = 0; g < NBG; g++) {
             const SGroup& G = p.bgroups[g];
-            if (G.ops & OPB_SUM) {
+            const uint32_t ops = (g == 0 && SH::BOPS >= 0) ? (uint32_t)SH::BOPS : G.ops;
+            if (ops & OPB_SUM) {
                 const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_sum[g]);
                 for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
                     uint64_t v = ss[i];
@@ -543,14 +603,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     }
                 }
             }
-            if (G.ops & OPB_MIN) {
+            if (ops & OPB_MIN) {
                 const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_min[g]);
                 for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
                     uint64_t v = ss[i];
                     if (v && __ldcg(G.acc_min + i) < v) atomicMax((unsigned long long*)(G.acc_min + i), (unsigned long long)v);
                 }
             }
-            if (G.ops & OPB_MAX) {
+            if (ops & OPB_MAX) {
                 const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_max[g]);
                 for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
                     uint64_t v = ss[i];
@@ -573,11 +633,12 @@ __global__ void k_present_from_counts(const uint64_t* __restrict__ counts, uint8
 // dense TERMS | HISTOGRAM over leaf metrics), every column single-valued.
 // ------------------------------------------------------------------------------------------------------
 typedef void (*stream_fn)(const SParams);
+// runtime-op-mask shapes: any flat plan
 template <int BUCKET, int NBG, int NRG>
 static stream_fn pick_flags(bool compact, bool stab) {
     if (BUCKET == BK_NONE) stab = false;
-    if (stab) return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true, (BUCKET != BK_NONE)> : (stream_fn)k_stream<BUCKET, NBG, NRG, false, (BUCKET != BK_NONE)>;
-    return compact ? (stream_fn)k_stream<BUCKET, NBG, NRG, true, false> : (stream_fn)k_stream<BUCKET, NBG, NRG, false, false>;
+    if (stab) return compact ? (stream_fn)k_stream<Shp<BUCKET, NBG, NRG, true, (BUCKET != BK_NONE)>> : (stream_fn)k_stream<Shp<BUCKET, NBG, NRG, false, (BUCKET != BK_NONE)>>;
+    return compact ? (stream_fn)k_stream<Shp<BUCKET, NBG, NRG, true, false>> : (stream_fn)k_stream<Shp<BUCKET, NBG, NRG, false, false>>;
 }
 template <int BUCKET, int NBG>
 static stream_fn pick_nrg(int nrg, bool compact, bool stab) {
@@ -592,11 +653,37 @@ static stream_fn pick_nbg(int nbg, int nrg, bool compact, bool stab) {
     switch (nbg) {
         case 0: return pick_nrg<BUCKET, 0>(nrg, compact, stab);
         case 1: return pick_nrg<BUCKET, 1>(nrg, compact, stab);
-        case 2: return pick_nrg<BUCKET, 2>(nrg, compact, stab);
         default: return pick_nrg<BUCKET, 3>(nrg, compact, stab);
     }
 }
-static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab) {
+// compile-time-op-mask shapes for the hot configurations (one bucket value column or one root column)
+template <int BUCKET, int BOPS>
+static stream_fn pick_ct_bucket(bool compact, bool stab) {
+    if (stab) return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, true, BOPS>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, true, BOPS>>;
+    return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, false, BOPS>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, false, BOPS>>;
+}
+template <int ROPS>
+static stream_fn pick_ct_root(bool compact) {
+    return compact ? (stream_fn)k_stream<Shp<BK_NONE, 0, 1, true, false, -1, ROPS>> : (stream_fn)k_stream<Shp<BK_NONE, 0, 1, false, false, -1, ROPS>>;
+}
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0) {
+    if (bucket == BK_TERMS && nbg == 1 && nrg == 0) {
+        switch (bops0) {
+            case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab);
+            case OPB_MAX: return pick_ct_bucket<BK_TERMS, OPB_MAX>(compact, stab);
+            case OPB_SUM: return pick_ct_bucket<BK_TERMS, OPB_SUM>(compact, stab);
+            case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab);
+        }
+    }
+    if (bucket == BK_NONE && nrg == 1) {
+        switch (rops0) {
+            case OPB_MIN: return pick_ct_root<OPB_MIN>(compact);
+            case OPB_MAX: return pick_ct_root<OPB_MAX>(compact);
+            case OPB_SUM: return pick_ct_root<OPB_SUM>(compact);
+            case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_root<(OPB_MIN | OPB_MAX | OPB_SUM)>(compact);
+        }
+    }
+    if (nbg == 2) nbg = 3;
     switch (bucket) {
         case BK_NONE: return pick_nrg<BK_NONE, 0>(nrg, compact, false);
         case BK_TERMS: return pick_nbg<BK_TERMS>(nbg, nrg, compact, stab);
@@ -671,6 +758,7 @@ int stream_try(ExecState& es) {
         if (sp.n_preds >= ST_MAXPRED) return false;
         int i = sp.n_preds++;
         sp.pred_type[i] = type;
+        if (type != PR_FILTER) sp.n_vpreds++;
         sp.pred_scol[i] = scol;
         sp.pred_lut[i] = lut;
         pred_src.push_back(src);
@@ -836,7 +924,8 @@ int stream_try(ExecState& es) {
     bool stab = false;
     if (bucket_mode != BK_NONE) {
         size_t tb = 0;
-        for (int c = 0; c < sp.n_bcounts; c++) { sp.soff_tab_count[c] = (uint32_t)tb; tb += ((sp.dom_size * 4 + 127) & ~127ull); }
+        // count table 0 always exists in a shared-table kernel: it records which buckets exist
+        for (int c = 0; c < std::max(sp.n_bcounts, 1); c++) { sp.soff_tab_count[c] = (uint32_t)tb; tb += ((sp.dom_size * 4 + 127) & ~127ull); }
         for (int g = 0; g < n_bgroups; g++) {
             if (sp.bgroups[g].ops & OPB_SUM) { sp.soff_tab_sum[g] = (uint32_t)tb; tb += ((sp.dom_size * 8 + 127) & ~127ull); }
             if (sp.bgroups[g].ops & OPB_MIN) { sp.soff_tab_min[g] = (uint32_t)tb; tb += ((sp.dom_size * 8 + 127) & ~127ull); }
@@ -862,11 +951,12 @@ int stream_try(ExecState& es) {
     sp.table_bytes = (uint32_t)table_bytes;
     size_t smem_bytes = table_bytes + (size_t)n_groups * sp.group_bytes;
     uint8_t* present = sp.present;
-    if (bucket_mode != BK_NONE && sp.n_bcounts > 0) sp.present = nullptr;  // derived from the counts below
+    sp.present_out = present;
+    if (bucket_mode != BK_NONE && (sp.n_bcounts > 0 || stab)) sp.present = nullptr;  // derived from the counts
 
     // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
     int nrg_t = n_rgroups <= 1 ? n_rgroups : ST_MAXRG;
-    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab);
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u);
     static std::mutex attr_mu;
     static std::vector<stream_fn> attr_done;
     {
@@ -888,7 +978,7 @@ int stream_try(ExecState& es) {
     if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
     es.ctx->launches++;
     es.n_launches++;
-    if (bucket_mode != BK_NONE && sp.n_bcounts > 0) {
+    if (bucket_mode != BK_NONE && sp.n_bcounts > 0 && !stab) {
         uint64_t n = es.scopes[bucket_scope].capacity;
         k_present_from_counts<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, es.st>>>(sp.bcount_acc[0], present, n);
         es.ctx->launches++;

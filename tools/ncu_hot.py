@@ -10,16 +10,26 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "tantivy_aggregations_b200", "libtagg.so")], cwd=tmp, capture_output=True)
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f"{cub}.sm_100a.cubin")], capture_output=True, text=True).stdout
-line_of, cur, infn = {}, None, False
-for l in dis.splitlines():
+def parse_lines(kern):
+  line_of, cur, infn = {}, None, False
+  for l in dis.splitlines():
     if l.startswith("//---------------------"): infn = kern in l
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m: line_of[int(m.group(1), 16)] = cur
+  return line_of
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+# exact function: "void k_stream<(int)1, (int)1, (int)0, (bool)1, (bool)1>(SParams)" -> _Z8k_streamILi1ELi1ELi0ELb1ELb1EEv7SParams
+demangled = rows[0][1]
+mt = re.match(r"void (\w+)<(.*)>\(", demangled)
+if mt:
+    args = "".join(("Li" if "int" in a else "Lb") + a.split(")")[1].strip() + "E" for a in mt.group(2).split(","))
+    kern = f"_Z{len(mt.group(1))}{mt.group(1)}I{args}E"
+    print("function", kern)
+line_of = parse_lines(kern)
 hi = next(i for i, r in enumerate(rows) if len(r) > 1 and r[1] == "Source")
 ix = {h: i for i, h in enumerate(rows[hi])}
 S, I = ix["# Samples"], ix["Instructions Executed"]
