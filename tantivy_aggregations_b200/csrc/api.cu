@@ -39,6 +39,33 @@ void tagg_ctx::release_stream(cudaStream_t s) {
     stream_pool.push_back(s);
 }
 
+CallRes* tagg_ctx::acquire_call() {
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!call_pool.empty()) {
+            CallRes* c = call_pool.back();
+            call_pool.pop_back();
+            c->pinned_used = 0;
+            return c;
+        }
+    }
+    auto* c = new CallRes();
+    c->st = acquire_stream();
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    c->pinned_bytes = 1 << 20;
+    if (cudaHostAlloc((void**)&c->pinned, c->pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        c->pinned = nullptr;
+        c->pinned_bytes = 0;
+        cudaGetLastError();
+    }
+    return c;
+}
+void tagg_ctx::release_call(CallRes* c) {
+    std::lock_guard<std::mutex> g(mu);
+    call_pool.push_back(c);
+}
+
 // ---- plan analysis ---------------------------------------------------------------------------------
 static int analyse(PlanMeta& m, uint32_t& pos, int parent, int scope, int depth) {
     uint32_t n = (uint32_t)m.nodes.size();
@@ -163,6 +190,15 @@ int tagg_ctx_create(int device, tagg_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    {   // keep freed stream-ordered allocations cached in the pool: by default they go back to the driver at
+        // every synchronisation and the next query pays for mapping them again
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (prop.major < 10) {
         delete c;
         return tagg_fail(TAGG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
@@ -175,6 +211,13 @@ int tagg_ctx_destroy(tagg_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     tagg_comm_destroy(ctx);
+    for (auto c : ctx->call_pool) {
+        cudaStreamDestroy(c->st);
+        cudaEventDestroy(c->ev0);
+        cudaEventDestroy(c->ev1);
+        if (c->pinned) cudaFreeHost(c->pinned);
+        delete c;
+    }
     for (auto s : ctx->stream_pool) cudaStreamDestroy(s);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     delete ctx;
@@ -205,9 +248,9 @@ int tagg_ctx_timer_start(tagg_ctx* ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!ctx->timer0) { CUDA_TRY(cudaEventCreate(&ctx->timer0)); CUDA_TRY(cudaEventCreate(&ctx->timer1)); }
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaStream_t st = ctx->acquire_stream();  // LIFO pool: the same stream the next execute will use
-    cudaError_t e = cudaEventRecord(ctx->timer0, st);
-    ctx->release_stream(st);
+    CallRes* cr = ctx->acquire_call();  // LIFO pool: the same stream the next execute will use
+    cudaError_t e = cudaEventRecord(ctx->timer0, cr->st);
+    ctx->release_call(cr);
     if (e != cudaSuccess) return tagg_fail(TAGG_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -215,9 +258,9 @@ int tagg_ctx_timer_start(tagg_ctx* ctx) {
 int tagg_ctx_timer_stop(tagg_ctx* ctx, double* ms) {
     if (!ctx || !ms || !ctx->timer0) return tagg_fail(TAGG_ERR_BAD_ARG, "timer not started");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->acquire_stream();
-    cudaError_t e = cudaEventRecord(ctx->timer1, st);
-    ctx->release_stream(st);
+    CallRes* cr = ctx->acquire_call();
+    cudaError_t e = cudaEventRecord(ctx->timer1, cr->st);
+    ctx->release_call(cr);
     if (e != cudaSuccess) return tagg_fail(TAGG_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
     CUDA_TRY(cudaEventSynchronize(ctx->timer1));
     float f = 0;

@@ -5,6 +5,10 @@
 #include <algorithm>
 #include <cmath>
 
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "exec.h"
 
 #define DENSE_MAX_BUCKETS (1ull << 24)
@@ -13,9 +17,17 @@
 
 ExecState::~ExecState() {
     free_temps();
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (st) ctx->release_stream(st);
+    if (call) {
+        cudaStreamSynchronize(st);  // the pinned block may still feed an in-flight copy
+        ctx->release_call(call);
+    }
+}
+const void* ExecState::pin(const void* src, size_t bytes) {
+    size_t at = (call->pinned_used + 63) & ~(size_t)63;
+    if (!call->pinned || at + bytes > call->pinned_bytes) return src;
+    memcpy(call->pinned + at, src, bytes);
+    call->pinned_used = at + bytes;
+    return call->pinned + at;
 }
 void ExecState::free_temps() {
     for (void* p : temps) cudaFreeAsync(p, st);
@@ -392,7 +404,7 @@ static int build_dev_plan(ExecState& es) {
     void* p = nullptr;
     CUDA_TRY(cudaMallocAsync(&p, sizeof(DevPlan), es.st));
     es.d_plan = (DevPlan*)p;
-    CUDA_TRY(cudaMemcpyAsync(es.d_plan, &P, sizeof(DevPlan), cudaMemcpyHostToDevice, es.st));
+    CUDA_TRY(cudaMemcpyAsync(es.d_plan, es.pin(&P, sizeof(DevPlan)), sizeof(DevPlan), cudaMemcpyHostToDevice, es.st));
     return 0;
 }
 
@@ -403,21 +415,31 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "tagg_execute_collective needs tagg_comm_init first");
 
+    static const bool trace = getenv("TAGG_TRACE") != nullptr;
+    auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tagg] %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_begin).count());
+    };
     ExecState es;
     es.ctx = ctx;
     es.plan = plan;
     es.meta = plan->meta.get();
     es.collective = collective;
-    es.st = ctx->acquire_stream();
-    CUDA_TRY(cudaEventCreate(&es.ev0));
-    CUDA_TRY(cudaEventCreate(&es.ev1));
+    es.call = ctx->acquire_call();
+    es.st = es.call->st;
+    es.ev0 = es.call->ev0;
+    es.ev1 = es.call->ev1;
 
+    lap("acquire");
     int rc = resolve_segments(es, inputs, n_inputs);
     if (rc) return rc;
+    lap("resolve_segments");
     if (n_inputs) {
         rc = dev_alloc(es, &es.d_segs, sizeof(DevSegment) * n_inputs);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.hsegs.data(), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
+        CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.pin(es.hsegs.data(), sizeof(DevSegment) * n_inputs), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
     }
 
     float ms_total = 0;
@@ -435,6 +457,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (rc) return rc;
         rc = build_dev_plan(es);
         if (rc) return rc;
+        lap("layout+plan");
 
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
         int handled = 0;
@@ -451,9 +474,23 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             }
         }
         CUDA_TRY(cudaEventRecord(es.ev1, es.st));
+        lap("launched");
         uint32_t overflow = 0;
-        CUDA_TRY(cudaMemcpyAsync(&overflow, es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
+        es.host_arena = nullptr;
+        // small arenas come back whole, in one pinned copy, together with the overflow flag
+        size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
+        bool whole = !collective && es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes;
+        if (whole) {
+            CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(&overflow, es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
+        }
         CUDA_TRY(cudaStreamSynchronize(es.st));
+        lap("synced");
+        if (whole) {
+            es.host_arena = es.call->pinned + at;
+            memcpy(&overflow, es.host_arena + es.off_overflow, 4);
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, es.ev0, es.ev1);
         ms_total += ms;
@@ -484,6 +521,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         delete res;
         return rc;
     }
+    lap("read_result");
     res->kernel_ms = ms_total;
     res->alg_bytes = es.alg_bytes;
     res->n_launches = es.n_launches;

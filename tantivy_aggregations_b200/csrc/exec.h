@@ -18,6 +18,8 @@ struct ExecState {
     const tagg_plan* plan = nullptr;
     const PlanMeta* meta = nullptr;
     cudaStream_t st = nullptr;
+    CallRes* call = nullptr;
+    const uint8_t* host_arena = nullptr;  // pinned copy of the accumulator arena (small arenas), valid after the sync
     bool collective = false;
 
     std::vector<const tagg_segment*> segs;
@@ -48,6 +50,8 @@ struct ExecState {
 
     ~ExecState();
     void free_temps();
+    // copy a small control block into pinned memory so its upload is asynchronous; falls back to `src`
+    const void* pin(const void* src, size_t bytes);
 };
 
 int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, bool collective,

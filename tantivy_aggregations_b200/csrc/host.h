@@ -25,6 +25,15 @@ int tagg_fail(int status, const char* fmt, ...);
     } while (0)
 
 // ---- handles ------------------------------------------------------------------------------------
+// Per-call host resources, pooled in the context: a stream, two events and a pinned staging block
+// (small control uploads and small result downloads go through pinned memory so they are truly async).
+struct CallRes {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t* pinned = nullptr;
+    size_t pinned_bytes = 0, pinned_used = 0;
+};
+
 struct tagg_ctx {
     int device = 0;
     int sm_count = 148;
@@ -37,8 +46,12 @@ struct tagg_ctx {
     void* nccl = nullptr;  // opaque NcclState*
     int rank = 0, n_ranks = 1;
 
+    std::vector<CallRes*> call_pool;
+
     cudaStream_t acquire_stream();
     void release_stream(cudaStream_t s);
+    CallRes* acquire_call();
+    void release_call(CallRes* c);
 };
 
 struct HostColumn {

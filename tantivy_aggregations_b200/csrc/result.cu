@@ -34,6 +34,11 @@ static int fetch(ExecState& es, const T* d_src, uint64_t capacity, const std::ve
                  std::vector<T>& out) {
     out.resize(raw.size());
     if (raw.empty()) return 0;
+    if (es.host_arena) {  // the whole arena is already on the host
+        const T* h = (const T*)(es.host_arena + ((const uint8_t*)d_src - es.arena));
+        for (size_t i = 0; i < raw.size(); i++) out[i] = h[raw[i]];
+        return 0;
+    }
     if (capacity <= FULL_COPY_MAX) {
         std::vector<T> full(capacity);
         CUDA_TRY(cudaMemcpyAsync(full.data(), d_src, capacity * sizeof(T), cudaMemcpyDeviceToHost, es.st));
@@ -126,21 +131,50 @@ int read_result(ExecState& es, tagg_result* res) {
         std::vector<uint64_t> keys;
         std::vector<uint32_t> praw;
         if (L.mode == SCOPE_DENSE) {
-            std::vector<uint8_t> present(L.capacity);
-            CUDA_TRY(cudaMemcpyAsync(present.data(), es.arena + L.off_present, L.capacity, cudaMemcpyDeviceToHost, es.st));
-            CUDA_TRY(cudaStreamSynchronize(es.st));
-            for (uint64_t i = 0; i < L.capacity; i++)
-                if (present[i]) raw[s].push_back((uint32_t)i);
+            std::vector<uint8_t> present_copy;
+            const uint8_t* present = nullptr;
+            if (es.host_arena) {
+                present = es.host_arena + L.off_present;
+            } else {
+                present_copy.resize(L.capacity);
+                CUDA_TRY(cudaMemcpyAsync(present_copy.data(), es.arena + L.off_present, L.capacity, cudaMemcpyDeviceToHost, es.st));
+                CUDA_TRY(cudaStreamSynchronize(es.st));
+                present = present_copy.data();
+            }
+            raw[s].reserve(4096);
+            {   // 8 flags at a time: most of a big table is empty
+                uint64_t i = 0;
+                for (; i + 8 <= L.capacity; i += 8) {
+                    uint64_t w;
+                    memcpy(&w, present + i, 8);
+                    if (!w) continue;
+                    for (int k = 0; k < 8; k++)
+                        if (present[i + k]) raw[s].push_back((uint32_t)(i + k));
+                }
+                for (; i < L.capacity; i++)
+                    if (present[i]) raw[s].push_back((uint32_t)i);
+            }
             keys.resize(raw[s].size());
             praw.resize(raw[s].size());
-            for (size_t i = 0; i < raw[s].size(); i++) {
-                keys[i] = L.dom_min + raw[s][i] % L.dom_size;
-                praw[i] = (uint32_t)(raw[s][i] / L.dom_size);
+            if (L.dom_size == L.capacity) {  // the parent scope has one bucket (the common flat shape)
+                for (size_t i = 0; i < raw[s].size(); i++) { keys[i] = L.dom_min + raw[s][i]; praw[i] = 0; }
+            } else {
+                for (size_t i = 0; i < raw[s].size(); i++) {
+                    keys[i] = L.dom_min + raw[s][i] % L.dom_size;
+                    praw[i] = (uint32_t)(raw[s][i] / L.dom_size);
+                }
             }
         } else {
-            std::vector<uint32_t> state(L.capacity);
-            CUDA_TRY(cudaMemcpyAsync(state.data(), es.arena + L.off_state, L.capacity * 4, cudaMemcpyDeviceToHost, es.st));
-            CUDA_TRY(cudaStreamSynchronize(es.st));
+            std::vector<uint32_t> state_copy;
+            const uint32_t* state = nullptr;
+            if (es.host_arena) {
+                state = (const uint32_t*)(es.host_arena + L.off_state);
+            } else {
+                state_copy.resize(L.capacity);
+                CUDA_TRY(cudaMemcpyAsync(state_copy.data(), es.arena + L.off_state, L.capacity * 4, cudaMemcpyDeviceToHost, es.st));
+                CUDA_TRY(cudaStreamSynchronize(es.st));
+                state = state_copy.data();
+            }
             for (uint64_t i = 0; i < L.capacity; i++)
                 if (state[i] == ST_READY) raw[s].push_back((uint32_t)i);
         }
@@ -158,10 +192,15 @@ int read_result(ExecState& es, tagg_result* res) {
         auto& S = res->scopes[s];
         S.keys.resize(keys.size());
         S.parents.resize(keys.size());
+        const bool single_parent = raw[ps].size() == 1 && raw[ps][0] == 0;
         for (size_t i = 0; i < keys.size(); i++) {
             S.keys[i] = nd.op == TAGG_OP_TERMS ? code_to_bits_h(nd.kind, keys[i]) : keys[i];
-            auto it = std::lower_bound(raw[ps].begin(), raw[ps].end(), praw[i]);
-            S.parents[i] = (uint32_t)(it - raw[ps].begin());
+            if (single_parent) {
+                S.parents[i] = 0;
+            } else {
+                auto it = std::lower_bound(raw[ps].begin(), raw[ps].end(), praw[i]);
+                S.parents[i] = (uint32_t)(it - raw[ps].begin());
+            }
         }
     }
     for (size_t k = 0; k < es.slots.size(); k++) {

@@ -909,7 +909,7 @@ int stream_try(ExecState& es) {
     SegDesc* d_descs = nullptr;
     if (cudaMallocAsync((void**)&d_descs, nseg * sizeof(SegDesc), es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "segment table allocation failed");
     es.temps.push_back(d_descs);
-    if (cudaMemcpyAsync(d_descs, descs.data(), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, es.st) != cudaSuccess)
+    if (cudaMemcpyAsync(d_descs, es.pin(descs.data(), nseg * sizeof(SegDesc)), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, es.st) != cudaSuccess)
         return -tagg_fail(TAGG_ERR_CUDA, "segment table upload failed");
     sp.segs = d_descs;
 

@@ -24,10 +24,10 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(out)))
 # exact function: "void k_stream<(int)1, (int)1, (int)0, (bool)1, (bool)1>(SParams)" -> _Z8k_streamILi1ELi1ELi0ELb1ELb1EEv7SParams
 demangled = rows[0][1]
-mt = re.match(r"void (\w+)<(.*)>\(", demangled)
+mt = re.match(r"void (\w+)<(?:Shp<)?(.*?)>+\(", demangled)
 if mt:
-    args = "".join(("Li" if "int" in a else "Lb") + a.split(")")[1].strip() + "E" for a in mt.group(2).split(","))
-    kern = f"_Z{len(mt.group(1))}{mt.group(1)}I{args}E"
+    args = "".join(("Li" if "int" in a else "Lb") + a.split(")")[1].strip().replace("-", "n") + "E" for a in mt.group(2).split(","))
+    kern = f"_Z{len(mt.group(1))}{mt.group(1)}I" + (f"3ShpI{args}E" if "Shp<" in demangled else args) + "E"
     print("function", kern)
 line_of = parse_lines(kern)
 hi = next(i for i, r in enumerate(rows) if len(r) > 1 and r[1] == "Source")
