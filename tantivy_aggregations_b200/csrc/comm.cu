@@ -14,7 +14,39 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "exec.h"
+
+// Small tables: every rank gathers all arenas (one collective) and reduces them itself, class by class, in rank
+// order — one NCCL call instead of one per reduction class, and bit-identical f64 sums on every rank.
+__global__ void k_reduce_gathered(const uint8_t* __restrict__ gathered, uint8_t* __restrict__ arena, size_t arena_bytes, int n_ranks,
+                                  size_t b0, size_t e0, size_t b1, size_t e1, size_t b2, size_t e2, size_t b3, size_t e3) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = b0 + t0; i < e0; i += stride) {  // existence / Option flags: max(u8)
+        uint8_t v = 0;
+        for (int r = 0; r < n_ranks; r++) v |= gathered[(size_t)r * arena_bytes + i];
+        arena[i] = v;
+    }
+    for (size_t i = b1 / 8 + t0; i < e1 / 8; i += stride) {  // counts, integer sums: wrapping sum(u64)
+        uint64_t v = 0;
+        for (int r = 0; r < n_ranks; r++) v += ((const uint64_t*)(gathered + (size_t)r * arena_bytes))[i];
+        ((uint64_t*)arena)[i] = v;
+    }
+    for (size_t i = b2 / 8 + t0; i < e2 / 8; i += stride) {  // f64 sums, folded in rank order
+        double v = 0.0;
+        for (int r = 0; r < n_ranks; r++) v = __dadd_rn(v, ((const double*)(gathered + (size_t)r * arena_bytes))[i]);
+        ((double*)arena)[i] = v;
+    }
+    for (size_t i = b3 / 8 + t0; i < e3 / 8; i += stride) {  // min / max on order-preserving codes: max(u64)
+        uint64_t v = 0;
+        for (int r = 0; r < n_ranks; r++) {
+            uint64_t x = ((const uint64_t*)(gathered + (size_t)r * arena_bytes))[i];
+            v = x > v ? x : v;
+        }
+        ((uint64_t*)arena)[i] = v;
+    }
+}
 
 struct NcclState {
     void* lib = nullptr;
@@ -23,6 +55,7 @@ struct NcclState {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -42,6 +75,7 @@ static int nccl_load(NcclState* s) {
     LOAD(CommInitRank, "ncclCommInitRank")
     LOAD(CommDestroy, "ncclCommDestroy")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(GetErrorString, "ncclGetErrorString")
@@ -127,22 +161,29 @@ int comm_merge_arena(ExecState& es) {
         if (L.mode != SCOPE_DENSE)
             return tagg_fail(TAGG_ERR_UNSUPPORTED, "collective merge of hashed bucket tables is not implemented yet (dense key domains only)");
     if (!m.pct_node.empty()) return tagg_fail(TAGG_ERR_UNSUPPORTED, "collective merge of percentiles is not implemented yet");
-    NCCL_TRY(s, s->GroupStart());
-    for (size_t sc = 1; sc < es.scopes.size(); sc++) {
-        const ScopeLayout& L = es.scopes[sc];
-        NCCL_TRY(s, s->AllReduce(es.arena + L.off_present, es.arena + L.off_present, L.capacity, ncclUint8, ncclMax, s->comm, es.st));
+    if (es.arena_bytes * (size_t)es.ctx->n_ranks <= (256u << 20)) {
+        uint8_t* gathered = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&gathered, es.arena_bytes * (size_t)es.ctx->n_ranks, es.st));
+        es.temps.push_back(gathered);
+        NCCL_TRY(s, s->AllGather(es.arena, gathered, es.arena_bytes, ncclUint8, s->comm, es.st));
+        size_t work = (es.cls_end[3] - es.cls_begin[0]) / 8 + 1;
+        unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)es.ctx->sm_count * 8);
+        k_reduce_gathered<<<blocks, 256, 0, es.st>>>(gathered, es.arena, es.arena_bytes, es.ctx->n_ranks, es.cls_begin[0], es.cls_end[0],
+                                                     es.cls_begin[1], es.cls_end[1], es.cls_begin[2], es.cls_end[2], es.cls_begin[3], es.cls_end[3]);
+        CUDA_TRY(cudaGetLastError());
+        es.ctx->launches++;
+        es.n_launches++;
+        return 0;
     }
-    for (size_t k = 0; k < es.slots.size(); k++) {
-        const SlotLayout& SL = es.slots[k];
-        const tagg_node& nd = m.nodes[m.slot_node[k]];
-        void* acc = es.arena + SL.off_acc;
-        if (nd.op == TAGG_OP_COUNT || (nd.op == TAGG_OP_SUM && nd.kind != TAGG_F64))
-            NCCL_TRY(s, s->AllReduce(acc, acc, SL.capacity, ncclUint64, ncclSum, s->comm, es.st));
-        else if (nd.op == TAGG_OP_SUM)
-            NCCL_TRY(s, s->AllReduce(acc, acc, SL.capacity, ncclFloat64, ncclSum, s->comm, es.st));
-        else
-            NCCL_TRY(s, s->AllReduce(acc, acc, SL.capacity, ncclUint64, ncclMax, s->comm, es.st));
-        NCCL_TRY(s, s->AllReduce(es.arena + SL.off_seen, es.arena + SL.off_seen, SL.capacity, ncclUint8, ncclMax, s->comm, es.st));
+    // the arena is laid out by reduction class (exec.cu layout_arena): one all-reduce per class
+    const ncclDataType_t dt[4] = {ncclUint8, ncclUint64, ncclFloat64, ncclUint64};
+    const ncclRedOp_t op[4] = {ncclMax, ncclSum, ncclSum, ncclMax};
+    const size_t esz[4] = {1, 8, 8, 8};
+    NCCL_TRY(s, s->GroupStart());
+    for (int c = 0; c < 4; c++) {
+        size_t bytes = es.cls_end[c] - es.cls_begin[c];
+        if (!bytes) continue;
+        NCCL_TRY(s, s->AllReduce(es.arena + es.cls_begin[c], es.arena + es.cls_begin[c], bytes / esz[c], dt[c], op[c], s->comm, es.st));
     }
     NCCL_TRY(s, s->GroupEnd());
     CUDA_TRY(cudaStreamSynchronize(es.st));

@@ -302,6 +302,9 @@ static int finalize_scopes(ExecState& es, const std::vector<uint64_t>& dom, cons
     return 0;
 }
 
+// The arena is laid out by reduction class so that a multi-GPU merge is at most four all-reduces:
+//   [control][hash scope tables][u8 max: bucket existence + Option flags][u64 sum: counts, integer sums]
+//   [f64 sum][u64 max: min / max (MIN stored complemented)]
 static int layout_arena(ExecState& es) {
     const PlanMeta& m = *es.meta;
     size_t off = 0;
@@ -309,10 +312,7 @@ static int layout_arena(ExecState& es) {
     off += 16;
     for (size_t s = 0; s < es.scopes.size(); s++) {
         ScopeLayout& L = es.scopes[s];
-        if (L.mode == SCOPE_DENSE) {
-            L.off_present = off;
-            off = align16(off + L.capacity);
-        } else {
+        if (L.mode == SCOPE_HASH) {
             L.off_keys = off; off = align16(off + L.capacity * 8);
             L.off_parents = off; off = align16(off + L.capacity * 4);
             L.off_state = off; off = align16(off + L.capacity * 4);
@@ -320,11 +320,24 @@ static int layout_arena(ExecState& es) {
         }
     }
     es.slots.assign(m.slot_node.size(), SlotLayout());
-    for (size_t k = 0; k < m.slot_node.size(); k++) {
-        SlotLayout& S = es.slots[k];
-        S.capacity = es.scopes[m.scope_of[m.slot_node[k]]].capacity;
-        S.off_acc = off; off = align16(off + S.capacity * 8);
-        S.off_seen = off; off = align16(off + S.capacity);
+    for (size_t k = 0; k < m.slot_node.size(); k++) es.slots[k].capacity = es.scopes[m.scope_of[m.slot_node[k]]].capacity;
+    es.cls_begin[0] = off;
+    for (size_t s = 0; s < es.scopes.size(); s++) {
+        ScopeLayout& L = es.scopes[s];
+        if (L.mode == SCOPE_DENSE) { L.off_present = off; off = align16(off + L.capacity); }
+    }
+    for (size_t k = 0; k < es.slots.size(); k++) { es.slots[k].off_seen = off; off = align16(off + es.slots[k].capacity); }
+    es.cls_end[0] = off;
+    for (int cls = 1; cls <= 3; cls++) {
+        es.cls_begin[cls] = off;
+        for (size_t k = 0; k < es.slots.size(); k++) {
+            const tagg_node& nd = m.nodes[m.slot_node[k]];
+            int c = (nd.op == TAGG_OP_COUNT || (nd.op == TAGG_OP_SUM && nd.kind != TAGG_F64)) ? 1 : (nd.op == TAGG_OP_SUM ? 2 : 3);
+            if (c != cls) continue;
+            es.slots[k].off_acc = off;
+            off = align16(off + es.slots[k].capacity * 8);
+        }
+        es.cls_end[cls] = off;
     }
     es.arena_bytes = off;
     void* p = nullptr;
@@ -448,8 +461,21 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         rc = scope_domains_local(es, dom, bounds);
         if (rc) return rc;
         if (collective) {
-            rc = comm_agree_domains(es, dom);
-            if (rc) return rc;
+            // the agreed domains only depend on the segments' column headers: remember them per segment set
+            std::vector<const void*> key(es.segs.begin(), es.segs.end());
+            std::vector<uint64_t> local = dom;
+            bool hit = false;
+            {
+                std::lock_guard<std::mutex> g(plan->mu);
+                if (plan->dom_key == key && plan->dom_local == local) { dom = plan->dom_agreed; hit = true; }
+            }
+            // every rank takes the same branch: the cache is filled by a collective call with the same inputs
+            if (!hit) {
+                rc = comm_agree_domains(es, dom);
+                if (rc) return rc;
+                std::lock_guard<std::mutex> g(plan->mu);
+                plan->dom_key = key; plan->dom_local = local; plan->dom_agreed = dom;
+            }
         }
         rc = finalize_scopes(es, dom, bounds);
         if (rc) return rc;
@@ -479,7 +505,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         es.host_arena = nullptr;
         // small arenas come back whole, in one pinned copy, together with the overflow flag
         size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
-        bool whole = !collective && es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes;
+        bool whole = !collective && es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes;  // (collective: after the merge)
         if (whole) {
             CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
         } else {
@@ -512,6 +538,12 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
     if (collective) {
         rc = comm_merge_arena(es);
         if (rc) return rc;
+        size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
+        if (es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes) {
+            CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaStreamSynchronize(es.st));
+            es.host_arena = es.call->pinned + at;
+        }
     }
 
     auto* res = new tagg_result();

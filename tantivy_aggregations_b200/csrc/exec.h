@@ -33,6 +33,7 @@ struct ExecState {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     size_t off_overflow = 0;
+    size_t cls_begin[4] = {0, 0, 0, 0}, cls_end[4] = {0, 0, 0, 0};  // arena regions by reduction class
     DevPlan hplan;
     DevPlan* d_plan = nullptr;
 

@@ -109,6 +109,10 @@ struct tagg_plan {
     tagg_ctx* ctx = nullptr;
     std::shared_ptr<PlanMeta> meta;
     std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
+    // multi-GPU: key domains agreed across ranks, cached per segment set (exec.cu)
+    mutable std::mutex mu;
+    mutable std::vector<const void*> dom_key;
+    mutable std::vector<uint64_t> dom_local, dom_agreed;
 };
 
 struct PctSummary {
