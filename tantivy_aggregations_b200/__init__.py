@@ -10,6 +10,7 @@ from ._ffi import DATE, F64, I64, U64, FastFieldNotAvailableError, TaggError
 from .agg import *  # noqa: F401,F403  (the reference's constructor functions)
 from .agg import Agg, eq, ge, gt, in_set, le, lt
 from .fruits import Histogram, Percentiles, Terms, canon, ckms_target_rank
+from .shard import assign_segments, merge_fruits
 from .index import (SINGLE_THREAD, THREAD_POOL, AllQuery, BitsetQuery, CachedQuery, Context, DocIdsQuery, Plan, RangeQuery,
                     ResultReader, Searcher, Segment, TermQuery)
 

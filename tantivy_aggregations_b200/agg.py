@@ -46,6 +46,15 @@ class Agg:
     def decode(self, reader, bucket):  # -> fruit of `bucket` (index into the enclosing scope)
         raise NotImplementedError
 
+    def create_fruit(self):
+        """`PreparedAgg::create_fruit` (src/agg.rs:23)."""
+        raise NotImplementedError
+
+    def merge(self, acc, fruit):
+        """`PreparedAgg::merge(&mut acc, fruit)` (src/agg.rs:27) on decoded fruits; returns the new acc.
+        Used when fruits of different processes are combined on the host (e.g. hashed bucket tables)."""
+        raise NotImplementedError
+
 
 def as_agg(a):
     if isinstance(a, Agg):
@@ -72,6 +81,12 @@ class TupleAgg(Agg):
     def decode(self, reader, bucket):
         return tuple(m.decode(reader, bucket) for m in self.members)
 
+    def create_fruit(self):
+        return tuple(m.create_fruit() for m in self.members)
+
+    def merge(self, acc, fruit):
+        return tuple(m.merge(a, f) for m, a, f in zip(self.members, acc, fruit))
+
 
 class CountAgg(Agg):
     """count_agg() — src/metric/count.rs:7-9; Fruit = u64"""
@@ -83,6 +98,12 @@ class CountAgg(Agg):
     def decode(self, reader, bucket):
         values, _ = reader.metric(self.node)
         return int(values[bucket])
+
+    def create_fruit(self):
+        return 0
+
+    def merge(self, acc, fruit):  # count.rs:39-41
+        return acc + fruit
 
 
 class _FoldAgg(Agg):
@@ -101,6 +122,23 @@ class _FoldAgg(Agg):
         if not seen[bucket]:
             return None
         return codec.bits_to_value(self.kind, values[bucket])
+
+    def create_fruit(self):
+        return None
+
+    def merge(self, acc, fruit):  # sum.rs:59-70, minmax.rs:59-72
+        if fruit is None:
+            return acc
+        if acc is None:
+            return fruit
+        if self.op == F.OP_SUM:
+            if self.kind == F.F64:
+                return acc + fruit
+            r = (acc + fruit) & ((1 << 64) - 1)  # wrapping, like release-mode Rust
+            return r - (1 << 64) if self.kind == F.I64 and r >> 63 else r
+        if self.op == F.OP_MIN:
+            return fruit if fruit < acc else acc
+        return fruit if fruit > acc else acc
 
 
 class SumAgg(_FoldAgg):
@@ -155,6 +193,14 @@ class TermsAgg(Agg):
             res[key] = self.sub.decode(reader, child)
         return Terms(res)
 
+    def create_fruit(self):
+        return Terms()
+
+    def merge(self, acc, fruit):  # terms.rs:85-92
+        for key, bucket in fruit.res.items():
+            acc.res[key] = self.sub.merge(acc.res[key] if key in acc.res else self.sub.create_fruit(), bucket)
+        return acc
+
 
 class HistogramAgg(Agg):
     """histogram_agg_f64(field, start, interval, sub) — src/bucket/histogram.rs:9-21"""
@@ -174,6 +220,15 @@ class HistogramAgg(Agg):
         return Histogram(self.start, self.interval,
                          {int(o): self.sub.decode(reader, c) for o, c in zip(ords, children)})
 
+    def create_fruit(self):
+        return Histogram(self.start, self.interval)
+
+    def merge(self, acc, fruit):  # histogram.rs:90-97
+        b = dict(acc._buckets)
+        for o, bucket in fruit._buckets.items():
+            b[o] = self.sub.merge(b[o] if o in b else self.sub.create_fruit(), bucket)
+        return Histogram(acc.start, acc.interval, b)
+
 
 class FilterAgg(Agg):
     """filter_agg(&query, sub) — src/filter.rs:8-16: narrows the doc stream by a second query."""
@@ -191,6 +246,12 @@ class FilterAgg(Agg):
 
     def decode(self, reader, bucket):
         return self.sub.decode(reader, bucket)
+
+    def create_fruit(self):
+        return self.sub.create_fruit()
+
+    def merge(self, acc, fruit):
+        return self.sub.merge(acc, fruit)
 
 
 # ---- predicates for post_filter_agg_* ---------------------------------------------------
@@ -307,6 +368,12 @@ class PostFilterAgg(Agg):
     def decode(self, reader, bucket):
         return self.sub.decode(reader, bucket)
 
+    def create_fruit(self):
+        return self.sub.create_fruit()
+
+    def merge(self, acc, fruit):
+        return self.sub.merge(acc, fruit)
+
 
 def _codes_to_bits(kind, codes):
     if kind == F.U64:
@@ -336,6 +403,12 @@ class GenericPostFilterAgg(Agg):
     def decode(self, reader, bucket):
         return self.sub.decode(reader, bucket)
 
+    def create_fruit(self):
+        return self.sub.create_fruit()
+
+    def merge(self, acc, fruit):
+        return self.sub.merge(acc, fruit)
+
 
 class EitherAgg(Agg):
     """either_agg / one_of_agg — src/either.rs: a runtime choice between two aggs, resolved on the
@@ -350,6 +423,15 @@ class EitherAgg(Agg):
     def decode(self, reader, bucket):
         f = self.agg.decode(reader, bucket)
         return (self.which, f) if self.tag else f
+
+    def create_fruit(self):
+        f = self.agg.create_fruit()
+        return (self.which, f) if self.tag else f
+
+    def merge(self, acc, fruit):
+        if self.tag:
+            return (self.which, self.agg.merge(acc[1], fruit[1]))
+        return self.agg.merge(acc, fruit)
 
 
 # ---- the reference's constructor functions --------------------------

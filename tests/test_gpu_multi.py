@@ -1,0 +1,59 @@
+"""GPU, >= 2 devices: segments sharded over ranks (one process per GPU), bucket tables merged by the
+NCCL exchange step (tagg_execute_collective), every rank's fruit equal to the single-process oracle.
+Skipped on a single-GPU box."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # host-side plumbing only (unique id broadcast)
+    import tantivy_aggregations_b200 as ta
+    from helpers import Corpus, assert_fruit_equal
+    from test_dist_gloo import build_corpus
+
+    corpus = build_corpus()
+    ox = corpus.build_oracle()
+    parts = ta.assign_segments([s.max_doc for s in corpus.segs], world)
+    ctx = ta.Context(rank)
+    ident = [ta.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    ctx.comm_init(ident[0], rank, world)
+    local = Corpus([corpus.segs[i] for i in parts[rank]]).build_gpu(ctx)
+    shapes = {
+        "scalars": lambda: (ta.count_agg(), ta.sum_agg_f64(2), ta.min_agg_f64(2), ta.max_agg_i64(3), ta.sum_agg_i64(3)),
+        "terms": lambda: ta.terms_agg_u64(1, (ta.count_agg(), ta.min_agg_f64(2), ta.max_agg_f64(2), ta.sum_agg_f64(2))),
+        "bench_shape": lambda: ta.filter_agg(ta.RangeQuery(3, ta.I64, 0, 49), (ta.count_agg(), ta.terms_agg_u64(1, (ta.count_agg(), ta.min_agg_f64(2))))),
+        "hist": lambda: ta.histogram_agg_f64(2, 0.0, 10.0, (ta.count_agg(), ta.sum_agg_f64(2))),
+        "nested_dense": lambda: ta.terms_agg_u64(1, ta.histogram_agg_f64(2, 0.0, 50.0, ta.count_agg())),
+        "multi": lambda: ta.terms_agg_u64s(4, (ta.count_agg(), ta.min_agg_f64(2))),
+    }
+    for name, mk in shapes.items():
+        want, _, _ = ox.search(ta.AllQuery(), mk(), mode=1, threads=2)
+        for path in (0, 1):
+            ctx.set_path(path)
+            got = local.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, collective=True)
+            assert_fruit_equal(got, want, 1e-12, f"{name}/path{path}/rank{rank}")
+    dist.barrier()
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write("ok")
+    dist.destroy_process_group()
+
+
+def test_collective_merge_matches_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
