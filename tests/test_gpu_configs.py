@@ -1,0 +1,197 @@
+"""GPU: BASELINE.json's five configurations at their FULL sizes, checked through size-independent
+properties (conservation of counts, agreement between independent kernels / table implementations,
+rank windows measured on the device) plus a bit-exact oracle comparison on a small extra segment of
+the same synthetic recipe (x(doc) = mix64(seed ^ tag ^ doc * GOLDEN), seed = 1)."""
+import numpy as np
+import pytest
+
+import tantivy_aggregations_b200 as ta
+from helpers import Corpus, SegSpec, assert_fruit_equal
+from tantivy_aggregations_b200 import _ffi as F
+
+pytestmark = pytest.mark.gpu
+
+SEED = 1
+STATUS, CATEGORY, PRICE, KEYS, VALS, KEYS_SPREAD = 0, 1, 2, 3, 4, 5
+T_STATUS, T_CAT, T_PRICE, T_KEYS, T_VALS = 11, 22, 33, 44, 55
+RTOL = 1e-12
+
+
+def synth_segments(ctx, n_docs, n_segs, cols, base0=0):
+    per = n_docs // n_segs
+    segs = []
+    for s in range(n_segs):
+        seg = ta.Segment(ctx, per, keep_host=False)
+        for c in cols:
+            c(seg, base0 + s * per)
+        segs.append(seg)
+    return segs
+
+
+def oracle_twin(n, base, cols):
+    """The same recipe on the host for one small segment -> (SegSpec, gpu-builder)."""
+    from oracle import oracle
+    s = SegSpec(n)
+    for kind, field, multi, args in cols:
+        if multi:
+            off, codes = oracle.synth_multi(args[0], SEED, args[1], base, n, *args[2:])
+            s.mcol_codes(field, kind, off, codes)
+        else:
+            s.col_codes(field, kind, oracle.synth_codes(args[0], SEED, args[1], base, n, *args[2:]))
+    return s
+
+
+def close(a, b, rtol=RTOL):
+    return abs(a - b) <= rtol * max(abs(a), abs(b))
+
+
+def test_c1_scalar_metrics_1m(ctx):
+    """C1: count + sum/min/max f64 over AllQuery, 1M-doc single segment — fully against the oracle."""
+    n = 1_000_000
+    spec = oracle_twin(n, 0, [(F.F64, PRICE, 0, (0, T_PRICE))])
+    corpus = Corpus([spec])
+    agg = lambda: (ta.count_agg(), ta.sum_agg_f64(PRICE), ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE))
+    want, _, _ = corpus.build_oracle().search(ta.AllQuery(), agg())
+    # device-generated column == host recipe, bit for bit
+    seg = ta.Segment(ctx, n)
+    seg.synth_column(PRICE, ta.F64, 0, SEED, T_PRICE, 0)
+    from oracle import oracle
+    assert seg.column_bytes(PRICE) == oracle.pack(spec.cols[PRICE][1])
+    assert seg.column_info(PRICE)["num_bits"] == 55
+    for path in (F.PATH_STREAM, F.PATH_GENERIC):
+        ctx.set_path(path)
+        try:
+            got = ta.Searcher(ctx, [seg]).agg_search(ta.AllQuery(), agg())
+        finally:
+            ctx.set_path(F.PATH_AUTO)
+        assert_fruit_equal(got, want, RTOL)
+
+
+def test_c2_filter_terms_100m(ctx):
+    """C2: filter_agg(status=0, (count, terms(category, (count, min price)))) on 100M docs, 10k categories."""
+    n, nseg, ncat = 100_000_000, 8, 10_000
+    segs = synth_segments(ctx, n, nseg, [
+        lambda s, b: s.synth_column(STATUS, ta.U64, 1, SEED, T_STATUS, b, 0, 4),
+        lambda s, b: s.synth_column(CATEGORY, ta.U64, 1, SEED, T_CAT, b, 1, ncat),
+        lambda s, b: s.synth_column(PRICE, ta.F64, 0, SEED, T_PRICE, b)])
+    S = ta.Searcher(ctx, segs)
+    fq = ta.TermQuery(STATUS, ta.U64, 0)
+    count, terms = S.agg_search(ta.AllQuery(), ta.filter_agg(fq, (ta.count_agg(), ta.terms_agg_u64(CATEGORY, (ta.count_agg(), ta.min_agg_f64(PRICE))))))
+    # conservation: every filtered doc lands in exactly one bucket; the filter is the device docset
+    assert count == sum(int(np.unpackbits(s.docset_to_bitset(fq.docset(s)), bitorder="little")[:s.max_doc].sum()) for s in segs)
+    assert sum(b[0] for b in terms.res.values()) == count and len(terms) == ncat
+    assert 0.2495 * n < count < 0.2505 * n
+    # min over buckets == scalar min under the same filter; and the generic kernel agrees on everything
+    assert min(b[1] for b in terms.res.values()) == S.agg_search(fq, ta.min_agg_f64(PRICE))
+    ctx.set_path(F.PATH_GENERIC)
+    try:
+        count2, terms2 = S.agg_search(ta.AllQuery(), ta.filter_agg(fq, (ta.count_agg(), ta.terms_agg_u64(CATEGORY, (ta.count_agg(), ta.min_agg_f64(PRICE))))))
+    finally:
+        ctx.set_path(F.PATH_AUTO)
+    assert count2 == count
+    assert_fruit_equal(terms2, terms)
+    for s in segs:
+        s.close()
+
+
+def test_c3_histogram_percentiles_500m(ctx):
+    """C3: histogram(price, 0, 10, count) + percentiles(price) over 500M docs, 50 % bitset."""
+    n, nseg = 500_000_000, 8
+    segs = synth_segments(ctx, n, nseg, [lambda s, b: s.synth_column(PRICE, ta.F64, 0, SEED, T_PRICE, b)])
+    S = ta.Searcher(ctx, segs)
+    rng = np.random.default_rng(3)
+    bits = {i: rng.integers(0, 256, size=(s.max_doc + 7) // 8, dtype=np.uint8) for i, s in enumerate(segs)}
+    n_sel = sum(int(np.unpackbits(b, bitorder="little")[:s.max_doc].sum()) for b, s in zip(bits.values(), segs))
+    q = ta.CachedQuery(ta.BitsetQuery(bits), segs)
+    hist, pct = S.agg_search(q, (ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)))
+    buckets = hist.buckets()
+    assert [k for k, _ in buckets] == [float(10 * i) for i in range(11)]
+    assert sum(c for _, c in buckets) == n_sel == pct.n
+    # each bucket's count == an independent range count on the device (codes are order preserving)
+    for key, c in buckets[:3] + buckets[-2:]:
+        lo, hi = max(key, 1.0), key + 10.0
+        got = S.agg_search(q, ta.post_filter_agg_f64(PRICE, ta.ge(lo), ta.post_filter_agg_f64(PRICE, ta.lt(hi), ta.count_agg())))
+        assert got == c, (key, got, c)
+    # percentiles: the answer's rank window, measured on the device, brackets the rank CKMS targets
+    eps = 0.01
+    for qq in (0.01, 0.25, 0.5, 0.75, 0.95, 0.99):
+        v = pct.percentile(qq)
+        below = S.agg_search(q, ta.post_filter_agg_f64(PRICE, ta.lt(v), ta.count_agg()))
+        upto = S.agg_search(q, ta.post_filter_agg_f64(PRICE, ta.le(v), ta.count_agg()))
+        assert upto > below, "the answer is an element of the input"
+        k = ta.ckms_target_rank(qq, n_sel)
+        band = eps * qq * n_sel + 1
+        assert below + 1 - band <= k <= upto + band, (qq, k, below, upto)
+    for s in segs:
+        s.close()
+    # bit-exact against the oracle on a small twin (same recipe, 300k docs, its own 50 % bitset)
+    m = 300_000
+    corpus = Corpus([oracle_twin(m, 7_000_000, [(F.F64, PRICE, 0, (0, T_PRICE))])])
+    sb = ta.BitsetQuery({0: rng.integers(0, 256, size=(m + 7) // 8, dtype=np.uint8)})
+    agg = lambda: (ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE))
+    want, _, _ = corpus.build_oracle().search(sb, agg())
+    got = corpus.build_gpu(ctx).agg_search(sb, agg())
+    assert_fruit_equal(got[0], want[0])
+    assert got[1].n == want[1].n
+
+
+def test_c4_multivalued_terms_1b_values(ctx):
+    """C4: terms_agg_u64s(keys, sum_agg_f64s(vals)): 250M docs, ~1e9 key values, 1M distinct keys.
+    The dense table (20-bit key domain) and the hashed spill table (the same keys spread over a 40-bit
+    domain) are two independent implementations that must agree bucket for bucket."""
+    n, nseg, nkeys, spread = 250_000_000, 16, 1_000_000, 1 << 20
+    segs = synth_segments(ctx, n, nseg, [
+        lambda s, b: s.synth_multicolumn(KEYS, ta.U64, 1, SEED, T_KEYS, b, 9, 0, nkeys),
+        lambda s, b: s.synth_multicolumn(KEYS_SPREAD, ta.U64, 2, SEED, T_KEYS, b, 9, 5, nkeys, spread),
+        lambda s, b: s.synth_multicolumn(VALS, ta.F64, 0, SEED, T_VALS, b, 3)])
+    S = ta.Searcher(ctx, segs)
+    n_key_values = sum(s.column_info(KEYS, 0)["n_values"] for s in segs)
+    assert 0.99e9 < n_key_values < 1.01e9
+    (dense, reader) = S.agg_search_with_executor(ta.AllQuery(), ta.terms_agg_u64s(KEYS, (ta.count_agg(), ta.sum_agg_f64s(VALS))),
+                                                 ta.SINGLE_THREAD, return_reader=True)
+    assert len(dense) == nkeys
+    assert sum(b[0] for b in dense.res.values()) == n_key_values  # once per value occurrence (terms.rs:172-179)
+    hashed = S.agg_search(ta.AllQuery(), ta.terms_agg_u64s(KEYS_SPREAD, (ta.count_agg(), ta.sum_agg_f64s(VALS))))
+    assert len(hashed) == nkeys
+    for k in list(dense.res)[:: nkeys // 5000]:
+        d, h = dense.res[k], hashed.res[5 + k * spread]
+        assert d[0] == h[0]
+        assert (d[1] is None) == (h[1] is None) and (d[1] is None or close(d[1], h[1]))
+    for s in segs:
+        s.close()
+    # bit-exact bucket structure / tolerance sums against the oracle on a small twin
+    m = 200_000
+    corpus = Corpus([oracle_twin(m, 123_000_000, [(F.U64, KEYS, 1, (1, T_KEYS, 9, 0, nkeys)), (F.F64, VALS, 1, (0, T_VALS, 3))])])
+    agg = lambda: ta.terms_agg_u64s(KEYS, sum_only())
+    sum_only = lambda: ta.sum_agg_f64s(VALS)
+    want, _, _ = corpus.build_oracle().search(ta.AllQuery(), agg())
+    got = corpus.build_gpu(ctx).agg_search(ta.AllQuery(), agg())
+    assert_fruit_equal(got, want, RTOL)
+
+
+def test_c5_post_filter_terms_1b(ctx):
+    """C5: post_filter(status == 0) -> terms(category 100k, (min, max, sum price)) over 1e9 docs in 64 segments."""
+    n, nseg, ncat = 1_000_000_000, 64, 100_000
+    segs = synth_segments(ctx, n, nseg, [
+        lambda s, b: s.synth_column(STATUS, ta.U64, 1, SEED, T_STATUS, b, 0, 4),
+        lambda s, b: s.synth_column(CATEGORY, ta.U64, 1, SEED, T_CAT, b, 1, ncat),
+        lambda s, b: s.synth_column(PRICE, ta.F64, 0, SEED, T_PRICE, b)])
+    S = ta.Searcher(ctx, segs)
+    pf = lambda sub: ta.post_filter_agg_u64(STATUS, ta.eq(0), sub)
+    terms, reader = S.agg_search_with_executor(ta.AllQuery(), pf(ta.terms_agg_u64(CATEGORY, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_f64(PRICE)))),
+                                               ta.SINGLE_THREAD, return_reader=True)
+    assert reader.stats()["path"] == 2 and len(terms) == ncat
+    cnt, mn, mx, sm = S.agg_search(ta.AllQuery(), pf((ta.count_agg(), ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_f64(PRICE))))
+    assert 0.2499 * n < cnt < 0.2501 * n
+    assert min(b[0] for b in terms.res.values()) == mn and max(b[1] for b in terms.res.values()) == mx
+    assert close(sum(b[2] for b in terms.res.values()), sm, 1e-10)
+    counts = S.agg_search(ta.AllQuery(), pf(ta.terms_agg_u64(CATEGORY, ta.count_agg())))
+    assert sum(counts.res.values()) == cnt and set(counts.res) == set(terms.res)
+    for s in segs:
+        s.close()
+    m = 250_000
+    corpus = Corpus([oracle_twin(m, 999_000_000, [(F.U64, STATUS, 0, (1, T_STATUS, 0, 4)), (F.U64, CATEGORY, 0, (1, T_CAT, 1, ncat)),
+                                                  (F.F64, PRICE, 0, (0, T_PRICE))])])
+    agg = lambda: pf(ta.terms_agg_u64(CATEGORY, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_f64(PRICE))))
+    want, _, _ = corpus.build_oracle().search(ta.AllQuery(), agg())
+    assert_fruit_equal(corpus.build_gpu(ctx).agg_search(ta.AllQuery(), agg()), want, RTOL)
