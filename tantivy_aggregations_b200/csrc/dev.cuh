@@ -122,7 +122,7 @@ struct DevNode {
     uint16_t own_scope;  // TERMS / HISTOGRAM: the scope this node keys
     uint16_t slot;       // leaf metrics: accumulator slot
     uint16_t aux;        // FILTER: filter index
-    uint32_t lut_bits_lo; // unused padding
+    uint32_t skip;       // 1: this sub-tree was handled by a streaming launch, the tree walker steps over it
     const uint8_t* lut;  // PRED_LUT bitmap (device)
     double f0, f1;
     uint64_t u0, u1;

@@ -347,6 +347,24 @@ static int layout_arena(ExecState& es) {
     return 0;
 }
 
+static int alloc_percentile_buffers(ExecState& es) {
+    const PlanMeta& m = *es.meta;
+    // percentile materialisation: capacity = every value that could be inserted
+    for (size_t k = 0; k < m.pct_node.size(); k++) {
+        const tagg_node& nd = m.nodes[m.pct_node[k]];
+        uint64_t cap = 0;
+        for (size_t i = 0; i < es.segs.size(); i++)
+            cap += nd.multi ? es.segs[i]->mcols.at(nd.field_id).second.n_values : es.n_cand[i];
+        es.pct_cap[k] = cap;
+        void* p = nullptr;
+        CUDA_TRY(cudaMallocAsync(&p, cap * 8 + 16, es.st)); es.pct_codes[k] = (uint64_t*)p;
+        CUDA_TRY(cudaMallocAsync(&p, cap * 4 + 16, es.st)); es.pct_buckets[k] = (uint32_t*)p;
+        CUDA_TRY(cudaMallocAsync(&p, 16, es.st)); es.pct_count[k] = (unsigned long long*)p;
+        CUDA_TRY(cudaMemsetAsync(es.pct_count[k], 0, 16, es.st));
+    }
+    return 0;
+}
+
 static int build_dev_plan(ExecState& es) {
     const PlanMeta& m = *es.meta;
     DevPlan& P = es.hplan;
@@ -365,6 +383,7 @@ static int build_dev_plan(ExecState& es) {
         d.own_scope = (uint16_t)(m.own_scope[i] < 0 ? 0 : m.own_scope[i]);
         d.slot = (uint16_t)(m.slot_of[i] < 0 ? 0 : m.slot_of[i]);
         d.aux = (uint16_t)(nd.op == TAGG_OP_PERCENTILES ? m.pct_of[i] : nd.aux);
+        d.skip = i < es.skip.size() ? es.skip[i] : 0;
         d.lut = (nd.op == TAGG_OP_POST_FILTER && nd.pred == TAGG_PRED_LUT) ? es.plan->d_blobs[nd.aux] : nullptr;
         d.f0 = nd.f0; d.f1 = nd.f1; d.u0 = nd.u0; d.u1 = nd.u1;
     }
@@ -397,22 +416,11 @@ static int build_dev_plan(ExecState& es) {
     }
     P.n_root_slots = nroot;
     P.overflow = (uint32_t*)(es.arena + es.off_overflow);
-    // percentile materialisation: capacity = every value that could be inserted
     for (size_t k = 0; k < m.pct_node.size(); k++) {
-        const tagg_node& nd = m.nodes[m.pct_node[k]];
-        uint64_t cap = 0;
-        for (size_t i = 0; i < es.segs.size(); i++)
-            cap += nd.multi ? es.segs[i]->mcols.at(nd.field_id).second.n_values : es.n_cand[i];
-        es.pct_cap[k] = cap;
-        void* p = nullptr;
-        CUDA_TRY(cudaMallocAsync(&p, cap * 8 + 16, es.st)); es.pct_codes[k] = (uint64_t*)p;
-        CUDA_TRY(cudaMallocAsync(&p, cap * 4 + 16, es.st)); es.pct_buckets[k] = (uint32_t*)p;
-        CUDA_TRY(cudaMallocAsync(&p, 16, es.st)); es.pct_count[k] = (unsigned long long*)p;
-        CUDA_TRY(cudaMemsetAsync(es.pct_count[k], 0, 16, es.st));
         P.pct_codes[k] = es.pct_codes[k];
         P.pct_buckets[k] = es.pct_buckets[k];
         P.pct_count[k] = es.pct_count[k];
-        P.pct_cap[k] = cap;
+        P.pct_cap[k] = es.pct_cap[k];
     }
     void* p = nullptr;
     CUDA_TRY(cudaMallocAsync(&p, sizeof(DevPlan), es.st));
@@ -481,23 +489,28 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (rc) return rc;
         rc = layout_arena(es);
         if (rc) return rc;
-        rc = build_dev_plan(es);
+        rc = alloc_percentile_buffers(es);
         if (rc) return rc;
-        lap("layout+plan");
+        lap("layout");
 
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
+        es.skip.assign(es.meta->nodes.size(), 0);
         int handled = 0;
         if (ctx->path != 1) {
             handled = stream_try(es);
             if (handled < 0) return -handled;
         }
-        if (!handled) {
+        if (handled != 1) {
             if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
-            es.path_used = 1;
+            es.path_used = handled == 2 ? 3 : 1;
+            rc = build_dev_plan(es);
+            if (rc) return rc;
             for (uint32_t i = 0; i < n_inputs; i++) {
                 CUDA_TRY(launch_generic(es.d_plan, es.d_segs + i, es.n_cand[i], ctx->sm_count, es.st));
                 if (es.n_cand[i]) { ctx->launches++; es.n_launches++; }
             }
+        } else {
+            es.path_used = 2;
         }
         CUDA_TRY(cudaEventRecord(es.ev1, es.st));
         lap("launched");

@@ -46,6 +46,7 @@ struct ExecState {
     uint64_t alg_bytes = 0;
     uint32_t n_launches = 0;
     uint32_t path_used = 0;
+    std::vector<uint8_t> skip;  // per plan node: sub-tree already handled by a streaming launch
     int hash_shift = 0;  // growth applied to hash scopes after an overflow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
             }
             if (!resumed && pc >= n_nodes) break;
             const DevNode& nd = P->nodes[pc];
+            if (nd.skip) { pc = nd.end; continue; }
             switch (nd.op) {
                 case TAGG_OP_TUPLE: pc++; break;
                 case TAGG_OP_COUNT: {  // count.rs:53-55
@@ -181,7 +182,13 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                     else { a = col_get(S.cols[nd.col], doc); b = col_get(S.cols[nd.col], (uint64_t)doc + 1); }
                     const DevColumn& vc = S.cols[nd.multi ? nd.col + 1 : nd.col];
                     for (uint64_t j = a; j < b; j++) {
-                        unsigned long long at = atomicAdd(P->pct_count[ps], 1ull);
+                        // warp-aggregated append: one atomic per converged group of lanes, not per value
+                        const unsigned grp = __activemask();
+                        const int leader = __ffs(grp) - 1;
+                        unsigned long long base = 0;
+                        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(P->pct_count[ps], (unsigned long long)__popc(grp));
+                        base = __shfl_sync(grp, base, leader);
+                        unsigned long long at = base + __popc(grp & ((1u << (threadIdx.x & 31)) - 1u));
                         if (at < P->pct_cap[ps]) {
                             P->pct_codes[ps][at] = col_get(vc, j);
                             P->pct_buckets[ps][at] = bucket;

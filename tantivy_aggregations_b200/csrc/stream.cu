@@ -731,9 +731,12 @@ static bool add_fold(ExecState& es, Shape& sh, SGroup* groups, int& n, int maxn,
     return true;
 }
 
-int stream_try(ExecState& es) {
+// One streaming launch over the members of the plan's top tuple that are not handled yet: the root
+// metrics (first launch only) and the first streamable bucket node.  Returns 1 if it launched (the
+// members it covered are flagged in es.skip), 0 if nothing is left that streams, < 0 on error.
+static int stream_launch(ExecState& es, bool first_launch) {
     const PlanMeta& m = *es.meta;
-    if (es.segs.empty() || !m.pct_node.empty()) return 0;
+    if (es.segs.empty()) return 0;
     Shape sh;
     SParams& sp = sh.sp;
     memset(&sp, 0, sizeof(sp));
@@ -802,26 +805,26 @@ int stream_try(ExecState& es) {
     } else {
         members.push_back(node);
     }
+    std::vector<uint32_t> covered;
     for (uint32_t mem : members) {
+        if (es.skip[mem]) continue;  // handled by an earlier launch
         const tagg_node& nd = m.nodes[mem];
         if (nd.op == TAGG_OP_COUNT) {
-            if (sp.n_root_counts >= 2) return 0;
+            if (!first_launch || sp.n_root_counts >= 2) continue;
             sp.root_count_acc[sp.n_root_counts++] = (uint64_t*)(es.arena + es.slots[m.slot_of[mem]].off_acc);
+            covered.push_back(mem);
         } else if (nd.op == TAGG_OP_SUM || nd.op == TAGG_OP_MIN || nd.op == TAGG_OP_MAX) {
-            if (!add_fold(es, sh, sp.rgroups, n_rgroups, ST_MAXRG, (int)mem)) return 0;
+            if (!first_launch) continue;
+            Shape save = sh;
+            int save_n = n_rgroups;
+            if (add_fold(es, sh, sp.rgroups, n_rgroups, ST_MAXRG, (int)mem)) covered.push_back(mem);
+            else { sh = save; n_rgroups = save_n; }
         } else if (nd.op == TAGG_OP_TERMS || nd.op == TAGG_OP_HISTOGRAM) {
-            if (bucket_mode != BK_NONE || nd.multi) return 0;
-            bucket_scope = m.own_scope[mem];
-            const ScopeLayout& L = es.scopes[bucket_scope];
-            if (L.mode != SCOPE_DENSE) return 0;
-            bucket_mode = nd.op == TAGG_OP_TERMS ? BK_TERMS : BK_HIST;
-            sp.key_scol = sh.stage_col(m.col_slot[mem]);
-            if (sp.key_scol < 0) return 0;
-            sp.dom_min = L.dom_min;
-            sp.dom_size = L.dom_size;
-            sp.f0 = nd.f0;
-            sp.f1 = nd.f1;
-            sp.present = es.arena + L.off_present;
+            if (bucket_mode != BK_NONE || nd.multi) continue;  // one bucket node per launch; multi-valued: generic kernel
+            const int sc = m.own_scope[mem];
+            const ScopeLayout& L = es.scopes[sc];
+            if (L.mode != SCOPE_DENSE) continue;
+            // the sub-tree must be count / sum / min / max leaves on single-valued columns
             uint32_t sub = mem + 1;
             std::vector<uint32_t> leaves;
             if (m.nodes[sub].op == TAGG_OP_TUPLE) {
@@ -829,21 +832,39 @@ int stream_try(ExecState& es) {
             } else {
                 leaves.push_back(sub);
             }
+            Shape save = sh;
+            int save_nb = n_bgroups;
+            bool ok = sh.stage_col(m.col_slot[mem]) >= 0;
+            int n_bc = 0;
+            uint64_t* bc_acc[2] = {nullptr, nullptr};
             for (uint32_t lf : leaves) {
+                if (!ok) break;
                 const tagg_node& ln = m.nodes[lf];
                 if (ln.op == TAGG_OP_COUNT) {
-                    if (sp.n_bcounts >= 2) return 0;
-                    sp.bcount_acc[sp.n_bcounts++] = (uint64_t*)(es.arena + es.slots[m.slot_of[lf]].off_acc);
+                    if (n_bc >= 2) ok = false;
+                    else bc_acc[n_bc++] = (uint64_t*)(es.arena + es.slots[m.slot_of[lf]].off_acc);
                 } else if (ln.op == TAGG_OP_SUM || ln.op == TAGG_OP_MIN || ln.op == TAGG_OP_MAX) {
-                    if (!add_fold(es, sh, sp.bgroups, n_bgroups, ST_MAXBG, (int)lf)) return 0;
+                    ok = add_fold(es, sh, sp.bgroups, n_bgroups, ST_MAXBG, (int)lf);
                 } else {
-                    return 0;
+                    ok = false;
                 }
             }
-        } else {
-            return 0;
+            if (!ok) { sh = save; n_bgroups = save_nb; continue; }
+            bucket_scope = sc;
+            bucket_mode = nd.op == TAGG_OP_TERMS ? BK_TERMS : BK_HIST;
+            sp.key_scol = sh.stage_col(m.col_slot[mem]);
+            sp.dom_min = L.dom_min;
+            sp.dom_size = L.dom_size;
+            sp.f0 = nd.f0;
+            sp.f1 = nd.f1;
+            sp.present = es.arena + L.off_present;
+            sp.n_bcounts = n_bc;
+            sp.bcount_acc[0] = bc_acc[0];
+            sp.bcount_acc[1] = bc_acc[1];
+            covered.push_back(mem);
         }
     }
+    if (covered.empty()) return 0;
 
     // stage layout: every staged column sized for its widest segment
     sp.n_cols = (int32_t)sh.staged.size();
@@ -904,7 +925,7 @@ int stream_try(ExecState& es) {
         for (size_t k = 0; k < es.slots.size(); k++)
             if (m.scope_of[m.slot_node[k]] == bucket_scope) es.slots[k].off_seen = es.scopes[bucket_scope].off_present;
     }
-    es.path_used = 2;
+    for (uint32_t mem : covered) es.skip[mem] = 1;
     if (sp.n_tiles == 0) return 1;
     SegDesc* d_descs = nullptr;
     if (cudaMallocAsync((void**)&d_descs, nseg * sizeof(SegDesc), es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "segment table allocation failed");
@@ -985,4 +1006,31 @@ int stream_try(ExecState& es) {
         es.n_launches++;
     }
     return 1;
+}
+
+// Runs as many streaming launches as the plan's top tuple needs (root metrics + one bucket node per
+// launch; every launch re-reads only the columns it uses).  Members that do not stream (multi-valued
+// fields, nested buckets, hashed scopes, percentiles) are left to the generic kernel: es.skip tells it
+// which sub-trees are already done.  Returns 1: everything streamed, 2: partly, 0: nothing, < 0: error.
+int stream_try(ExecState& es) {
+    const PlanMeta& m = *es.meta;
+    es.skip.assign(m.nodes.size(), 0);
+    int launches = 0;
+    for (int i = 0; i < 8; i++) {
+        int rc = stream_launch(es, i == 0);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+        launches++;
+    }
+    if (!launches) return 0;
+    // which top-level members are left?
+    uint32_t node = 0;
+    while (node < m.nodes.size() && (m.nodes[node].op == TAGG_OP_FILTER || m.nodes[node].op == TAGG_OP_POST_FILTER)) node++;
+    bool all = true;
+    if (m.nodes[node].op == TAGG_OP_TUPLE) {
+        for (uint32_t c = node + 1; c < m.end[node]; c = m.end[c]) all = all && es.skip[c];
+    } else {
+        all = es.skip[node];
+    }
+    return all ? 1 : 2;
 }
