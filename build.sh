@@ -19,3 +19,6 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $OBJ/api.o $OBJ/exec.o $OBJ/generic.o $OBJ/stream.o $OBJ/columns.o $OBJ/result.o $OBJ/comm.o $OBJ/docset.o -lcudart -ldl
 make -s -C oracle
 echo "built $OUT"
+# typed C++ host facade: compile its test driver (host-only code over the C ABI)
+g++ -O2 -std=c++17 -Wall -Iinclude -o tests/cpp/test_reference.bin tests/cpp/test_reference.cpp -Ltantivy_aggregations_b200 -ltagg -Wl,-rpath,'$ORIGIN/../../tantivy_aggregations_b200' -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64
+echo "built tests/cpp/test_reference.bin"
