@@ -51,8 +51,11 @@ CallRes* tagg_ctx::acquire_call() {
     }
     auto* c = new CallRes();
     c->st = acquire_stream();
+    c->st2 = acquire_stream();
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    for (auto& e : c->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming);
     c->pinned_bytes = 1 << 20;
     if (cudaHostAlloc((void**)&c->pinned, c->pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
         c->pinned = nullptr;
@@ -213,6 +216,9 @@ int tagg_ctx_destroy(tagg_ctx* ctx) {
     tagg_comm_destroy(ctx);
     for (auto c : ctx->call_pool) {
         cudaStreamDestroy(c->st);
+        cudaStreamDestroy(c->st2);
+        for (auto e : c->chunk_ev) cudaEventDestroy(e);
+        cudaEventDestroy(c->join_ev);
         cudaEventDestroy(c->ev0);
         cudaEventDestroy(c->ev1);
         if (c->pinned) cudaFreeHost(c->pinned);

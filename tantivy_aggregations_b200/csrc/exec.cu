@@ -18,7 +18,8 @@
 ExecState::~ExecState() {
     free_temps();
     if (call) {
-        cudaStreamSynchronize(st);  // the pinned block may still feed an in-flight copy
+        cudaStreamSynchronize(call->st2);  // host docsets are borrowed for the duration of the call only
+        cudaStreamSynchronize(st);         // the pinned block may still feed an in-flight copy
         ctx->release_call(call);
     }
 }
@@ -80,7 +81,7 @@ static int dev_alloc(ExecState& es, T** out, size_t bytes) {
 }
 
 // A docset argument -> what the kernels test (dev.cuh DevDocset).
-static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_docset& in, bool is_main,
+static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg_index, const tagg_docset& in, bool is_main,
                             DevSegment& hs, int& next_col, DevDocset* out, uint64_t* n_cand) {
     DevDocset d;
     memset(&d, 0, sizeof(d));
@@ -99,7 +100,7 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_d
             int rc = dev_alloc(es, &w, words * 4);
             if (rc) return rc;
             { size_t tail = need / 4; CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st)); }
-            if (need) CUDA_TRY(cudaMemcpyAsync(w, in.data, need, cudaMemcpyHostToDevice, es.st));
+            if (need) es.uploads.push_back({w, in.data, need, seg_index, nullptr, 0});
             d.kind = DS_BITSET;
             d.words = w;
             if (n_cand) *n_cand = seg->max_doc;
@@ -121,22 +122,22 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, const tagg_d
             uint32_t* ids = nullptr;
             int rc = dev_alloc(es, &ids, in.n * 4);
             if (rc) return rc;
-            if (in.n) CUDA_TRY(cudaMemcpyAsync(ids, in.data, in.n * 4, cudaMemcpyHostToDevice, es.st));
+            uint32_t* scatter = nullptr;
+            if (!is_main) {  // filters are tested per doc: the ids are scattered into a bitset (K6) right after their upload
+                rc = dev_alloc(es, &scatter, words * 4);
+                if (rc) return rc;
+                CUDA_TRY(cudaMemsetAsync(scatter, 0, words * 4, es.st));
+            }
+            if (in.n) es.uploads.push_back({ids, in.data, (size_t)in.n * 4, seg_index, scatter, in.n});
             es.alg_bytes += in.n * 4;
             if (is_main) {
                 d.kind = DS_IDS;
                 d.ids = ids;
                 d.n = in.n;
                 if (n_cand) *n_cand = in.n;
-            } else {  // filters are tested per doc: scatter the ids into a bitset (K6)
-                uint32_t* w = nullptr;
-                rc = dev_alloc(es, &w, words * 4);
-                if (rc) return rc;
-                CUDA_TRY(cudaMemsetAsync(w, 0, words * 4, es.st));
-                CUDA_TRY(launch_ids_to_bitset(ids, in.n, w, es.st));
-                if (in.n) { es.ctx->launches++; es.n_launches++; }
+            } else {
                 d.kind = DS_BITSET;
-                d.words = w;
+                d.words = scatter;
             }
             break;
         }
@@ -172,6 +173,18 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
     const PlanMeta& m = *es.meta;
     es.hsegs.resize(n_inputs);
     es.n_cand.assign(n_inputs, 0);
+    // host docsets to upload?  then pipeline: chunks of segments, kernels of a chunk start as soon as its docsets landed
+    {
+        uint64_t h2d = 0;
+        for (uint32_t i = 0; i < n_inputs; i++) {
+            auto bytes = [](const tagg_docset& d) { return d.kind == TAGG_DOCSET_BITSET ? d.n : d.kind == TAGG_DOCSET_SORTED_IDS ? d.n * 4 : 0; };
+            h2d += bytes(inputs[i].docset);
+            for (uint32_t f = 0; f < m.n_filters && f < inputs[i].n_filters; f++) h2d += bytes(inputs[i].filters[f]);
+        }
+        es.n_chunks = (h2d >= (1u << 20) && n_inputs >= 2) ? std::min<uint32_t>(4, n_inputs) : 1;
+        es.chunk_begin.assign(es.n_chunks + 1, 0);
+        for (uint32_t c = 0; c <= es.n_chunks; c++) es.chunk_begin[c] = (uint32_t)((uint64_t)n_inputs * c / es.n_chunks);
+    }
     for (uint32_t i = 0; i < n_inputs; i++) {
         const tagg_segment* seg = inputs[i].segment;
         if (!seg) return tagg_fail(TAGG_ERR_BAD_ARG, "input %u: null segment", i);
@@ -204,12 +217,34 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
             }
         }
         int next_col = at;
-        int rc = normalise_docset(es, seg, inputs[i].docset, true, hs, next_col, &hs.main, &es.n_cand[i]);
+        int rc = normalise_docset(es, seg, i, inputs[i].docset, true, hs, next_col, &hs.main, &es.n_cand[i]);
         if (rc) return rc;
         for (uint32_t f = 0; f < m.n_filters; f++) {
-            rc = normalise_docset(es, seg, inputs[i].filters[f], false, hs, next_col, &hs.filters[f], nullptr);
+            rc = normalise_docset(es, seg, i, inputs[i].filters[f], false, hs, next_col, &hs.filters[f], nullptr);
             if (rc) return rc;
         }
+    }
+    return 0;
+}
+
+// Host docsets cross PCIe on the upload stream, chunk by chunk; chunk_ev[c] fires when chunk c has landed.
+static int issue_uploads(ExecState& es) {
+    if (es.uploads.empty()) { es.n_chunks = 1; return 0; }
+    cudaStream_t up = es.call->st2;
+    CUDA_TRY(cudaEventRecord(es.call->join_ev, es.st));  // allocations / tail memsets issued so far
+    CUDA_TRY(cudaStreamWaitEvent(up, es.call->join_ev, 0));
+    size_t at = 0;
+    for (uint32_t c = 0; c < es.n_chunks; c++) {
+        for (; at < es.uploads.size() && es.uploads[at].seg < es.chunk_begin[c + 1]; at++) {
+            auto& u = es.uploads[at];
+            CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, up));
+            if (u.scatter_words) {
+                CUDA_TRY(launch_ids_to_bitset((const uint32_t*)u.dst, u.scatter_n, u.scatter_words, up));
+                es.ctx->launches++;
+                es.n_launches++;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(es.call->chunk_ev[c], up));
     }
     return 0;
 }
@@ -463,6 +498,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.pin(es.hsegs.data(), sizeof(DevSegment) * n_inputs), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
     }
 
+    rc = issue_uploads(es);
+    if (rc) return rc;
     float ms_total = 0;
     for (int attempt = 0;; attempt++) {
         std::vector<uint64_t> dom, bounds;
@@ -505,6 +542,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             es.path_used = handled == 2 ? 3 : 1;
             rc = build_dev_plan(es);
             if (rc) return rc;
+            if (!es.uploads.empty())
+                for (uint32_t c = 0; c < es.n_chunks; c++) CUDA_TRY(cudaStreamWaitEvent(es.st, es.call->chunk_ev[c], 0));
             for (uint32_t i = 0; i < n_inputs; i++) {
                 CUDA_TRY(launch_generic(es.d_plan, es.d_segs + i, es.n_cand[i], ctx->sm_count, es.st));
                 if (es.n_cand[i]) { ctx->launches++; es.n_launches++; }

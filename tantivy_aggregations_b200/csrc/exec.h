@@ -46,6 +46,12 @@ struct ExecState {
     uint64_t alg_bytes = 0;
     uint32_t n_launches = 0;
     uint32_t path_used = 0;
+    // chunked execute: host docsets are uploaded on a second stream, segments grouped into chunks; the kernels of
+    // chunk c wait only for chunk c's uploads (chunk_ev[c]) while later chunks are still crossing PCIe
+    struct PendingUpload { void* dst; const void* src; size_t bytes; uint32_t seg; uint32_t* scatter_words; uint64_t scatter_n; };
+    std::vector<PendingUpload> uploads;  // host docsets: issued on call->st2 (the upload stream) after the allocations
+    uint32_t n_chunks = 1;
+    std::vector<uint32_t> chunk_begin;  // n_chunks + 1 segment indices
     std::vector<uint8_t> skip;  // per plan node: sub-tree already handled by a streaming launch
     int hash_shift = 0;  // growth applied to hash scopes after an overflow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -28,8 +28,10 @@ int tagg_fail(int status, const char* fmt, ...);
 // Per-call host resources, pooled in the context: a stream, two events and a pinned staging block
 // (small control uploads and small result downloads go through pinned memory so they are truly async).
 struct CallRes {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;   // uploads, downloads, ordering
+    cudaStream_t st2 = nullptr;  // upload stream: host docsets cross PCIe here while kernels of earlier chunks run on st
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev = nullptr;
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0, pinned_used = 0;
 };

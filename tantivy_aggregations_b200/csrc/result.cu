@@ -6,6 +6,9 @@
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 #include <unordered_map>
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "exec.h"
 
@@ -114,6 +117,11 @@ static int read_percentiles(ExecState& es, tagg_result* res) {
 }
 
 int read_result(ExecState& es, tagg_result* res) {
+    static const bool trace = getenv("TAGG_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) fprintf(stderr, "[tagg]   read:%-12s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    };
     const PlanMeta& m = *es.meta;
     size_t ns = es.scopes.size();
     res->scopes.assign(ns, tagg_result::Scope());
@@ -203,6 +211,7 @@ int read_result(ExecState& es, tagg_result* res) {
             }
         }
     }
+    lap("scopes");
     for (size_t k = 0; k < es.slots.size(); k++) {
         const SlotLayout& SL = es.slots[k];
         int node = m.slot_node[k];
@@ -223,6 +232,7 @@ int read_result(ExecState& es, tagg_result* res) {
             if (!R.seen[i] && nd.op != TAGG_OP_COUNT) R.values[i] = 0;
         }
     }
+    lap("slots");
     return read_percentiles(es, res);
 }
 

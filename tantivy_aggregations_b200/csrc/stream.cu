@@ -68,6 +68,7 @@ struct SGroup {
 struct SParams {
     const SegDesc* segs;
     uint32_t n_segs, n_tiles;
+    uint32_t tile_base;  // tile_begin of the first segment of this launch (chunked execute)
     int32_t n_cols;
     uint32_t soff_col[ST_MAXCOLS];  // byte offset of each staged column inside a stage
     uint32_t soff_bits;             // bitset slots (256 B each) inside a stage
@@ -257,9 +258,10 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         bool first_lap = true;
         for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
             if (!first_lap) mbar_wait(empty + stage, parity);
-            while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= tile) cur_seg++;
+            const uint32_t gt = (uint32_t)tile + p.tile_base;  // tile index over the whole call
+            while (cur_seg + 1 < p.n_segs && p.segs[cur_seg + 1].tile_begin <= gt) cur_seg++;
             const SegDesc* Sg = p.segs + cur_seg;
-            const uint32_t lt = (uint32_t)tile - Sg->tile_begin;
+            const uint32_t lt = gt - Sg->tile_begin;
             const uint32_t flags = Sg->flags;
             TileDesc* T = tdesc + stage;
             uint8_t* base = stages + (size_t)stage * p.stage_bytes;
@@ -992,13 +994,30 @@ static int stream_launch(ExecState& es, bool first_launch) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, threads, smem_bytes) != cudaSuccess || per_sm < 1)
         return -tagg_fail(TAGG_ERR_CUDA, "k_stream does not fit an SM (%zu bytes of shared memory)", smem_bytes);
-    uint64_t work_units = ((uint64_t)sp.n_tiles + n_groups - 1) / n_groups;
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, work_units);
-    fn<<<grid, threads, smem_bytes, es.st>>>(sp);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
-    es.ctx->launches++;
-    es.n_launches++;
+    // one launch per chunk of segments: with host docsets being uploaded (on the upload stream), chunk c's kernel
+    // waits only for its own uploads and runs while later chunks are still crossing PCIe
+    const bool piped = !es.uploads.empty();
+    cudaStream_t kst = es.st;
+    for (uint32_t c = 0; c < es.n_chunks; c++) {
+        const uint32_t s0 = es.chunk_begin[c], s1 = es.chunk_begin[c + 1];
+        if (s0 == s1) continue;
+        SParams cp = sp;
+        cp.segs = d_descs + s0;
+        cp.n_segs = s1 - s0;
+        const uint32_t t0 = descs[s0].tile_begin;
+        const uint32_t t1 = s1 < nseg ? descs[s1].tile_begin : sp.n_tiles;
+        cp.n_tiles = t1 - t0;
+        cp.tile_base = t0;
+        if (cp.n_tiles == 0) continue;
+        if (piped && cudaStreamWaitEvent(kst, es.call->chunk_ev[c], 0) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "stream ordering failed");
+        uint64_t work_units = ((uint64_t)cp.n_tiles + n_groups - 1) / n_groups;
+        uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, work_units);
+        fn<<<grid, threads, smem_bytes, kst>>>(cp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
+        es.ctx->launches++;
+        es.n_launches++;
+    }
     if (bucket_mode != BK_NONE && sp.n_bcounts > 0 && !stab) {
         uint64_t n = es.scopes[bucket_scope].capacity;
         k_present_from_counts<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1024), 256, 0, es.st>>>(sp.bcount_acc[0], present, n);
