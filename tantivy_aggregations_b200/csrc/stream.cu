@@ -45,7 +45,7 @@
 
 enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2 };
 enum { OPB_SUM = 1, OPB_MIN = 2, OPB_MAX = 4 };
-enum { BK_NONE = 0, BK_TERMS = 1, BK_HIST = 2 };
+enum { BK_NONE = 0, BK_TERMS = 1, BK_HIST = 2, BK_RANK = 3 };
 enum { SF_MAIN_BITS = 1, SF_DELETES = 2, SF_PRED_BITS0 = 4 /* << i */, SF_PRED_NONE0 = 256 /* << i */ };
 
 // Everything the kernel needs to know about one segment, prepared on the host.
@@ -87,6 +87,14 @@ struct SParams {
     int32_t key_scol;
     uint64_t dom_min, dom_size;
     double f0, f1;
+    // BK_RANK (percentiles): rank bins delimited by sorted code boundaries (bounds[0] = tail threshold); codes below
+    // the threshold are appended to an exact tail list instead
+    const uint64_t* rank_bounds;
+    uint32_t soff_rank_bounds;
+    uint64_t* tail_codes;
+    unsigned long long* tail_count;
+    uint64_t tail_cap;
+    uint32_t* overflow_flag;
     uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
     uint8_t* present_out;  // STAB: written by the final table merge
     int32_t n_bcounts;
@@ -242,6 +250,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
     if (STAB) {
         uint32_t* t32 = (uint32_t*)smem;
         for (uint32_t i = tid; i < p.table_bytes / 4; i += blockDim.x) t32[i] = 0;
+        if (BUCKET == BK_RANK) {
+            __syncthreads();
+            uint64_t* b = (uint64_t*)(smem + p.soff_rank_bounds);
+            for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x) b[i] = p.rank_bounds[i];
+        }
     }
     __syncthreads();
 
@@ -402,20 +415,55 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 }
                 if (BUCKET != BK_NONE) {
                     uint32_t rel[U];
+                    bool tail[U];
+                    uint64_t tail_code[U];
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         rel[u] = 0;
+                        tail[u] = false;
+                        tail_code[u] = 0;
                         if (act[u]) {
                             if (BUCKET == BK_TERMS) {
                                 uint32_t lo, hi;
                                 tdelta(kc, dl[u], lo, hi);
                                 rel[u] = lo + krel;
                                 act[u] = rel[u] < dom_size32;
+                            } else if (BUCKET == BK_RANK) {
+                                // rank bin = last boundary <= code (branch-free binary search in shared memory)
+                                const uint64_t code = tget(kc, dl[u]);
+                                const uint32_t bsa = smem_saddr + p.soff_rank_bounds;
+                                uint32_t lo = 0, len = dom_size32;
+                                while (len > 1) {
+                                    const uint32_t half = len >> 1;
+                                    if (lds64(bsa + 8 * (lo + half)) <= code) lo += half;
+                                    len -= half;
+                                }
+                                rel[u] = lo;
+                                tail[u] = code < lds64(bsa);
+                                tail_code[u] = code;
                             } else {
                                 uint64_t ord;
                                 // NaN or below start: skipped (histogram.rs:138-145)
                                 if (hist_ord(tget(kc, dl[u]), p.f0, p.f1, &ord) && ord >= p.dom_min && ord - p.dom_min < p.dom_size) rel[u] = (uint32_t)(ord - p.dom_min);
                                 else act[u] = false;
+                            }
+                        }
+                    }
+                    if (BUCKET == BK_RANK) {
+                        // values below the first boundary go to the exact tail list: one atomic per warp and slot
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const uint32_t tm = __ballot_sync(0xffffffffu, tail[u]);
+                            if (tm) {
+                                unsigned long long base = 0;
+                                if (lane == (uint32_t)(__ffs(tm) - 1)) base = atomicAdd(p.tail_count, (unsigned long long)__popc(tm));
+                                base = __shfl_sync(0xffffffffu, base, __ffs(tm) - 1);
+                                if (tail[u]) {
+                                    const unsigned long long at = base + __popc(tm & lt_mask);
+                                    if (at < p.tail_cap) p.tail_codes[at] = tail_code[u];
+                                    else *p.overflow_flag = 3u;
+                                    act[u] = false;
+                                }
                             }
                         }
                     }
@@ -677,6 +725,7 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
             case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab);
         }
     }
+    if (bucket == BK_RANK) return pick_ct_bucket<BK_RANK, (OPB_MIN | OPB_MAX)>(compact, true);
     if (bucket == BK_NONE && nrg == 1) {
         switch (rops0) {
             case OPB_MIN: return pick_ct_root<OPB_MIN>(compact);

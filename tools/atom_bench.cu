@@ -45,6 +45,10 @@ template<int MODE> void run(const char* name, uint32_t nkeys, int threads, int c
     cudaFree(g);
 }
 int main() {
+    for (uint32_t nk : {10000u, 100000u, 1000000u, 16000000u}) {
+        run<G_RED64>("g_red64", nk, 256, 8); run<G_ADDF64>("g_addf64", nk, 256, 8); run<G_RED32>("g_red32", nk, 256, 8);
+        run<G_ADDF64>("g_addf64", nk, 512, 4);
+    }
     for (uint32_t nk : {11u, 1000u, 10000u, 100000u, 1000000u}) {
         run<G_MINCHK64>("g_minchk64", nk, 256, 8); run<G_MINCHK64_CG>("g_minchk_cg", nk, 256, 8); run<G_LD_CG>("g_ld_cg", nk, 256, 8); run<G_LD_CA>("g_ld_ca", nk, 256, 8);
     }
