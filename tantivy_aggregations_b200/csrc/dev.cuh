@@ -143,6 +143,53 @@ struct DevScope {
     unsigned long long* used;  // hash: claimed slots
 };
 
+#define INVALID_BUCKET 0xFFFFFFFFu
+
+__device__ __forceinline__ uint64_t hash_key(uint64_t key, uint32_t parent) {
+    return mix64(key ^ ((uint64_t)parent * 0x9E3779B97F4A7C15ull));
+}
+
+// `entry(key).or_insert_with(create_fruit)` (terms.rs:129-130, histogram.rs:148-149):
+// bucket index of (parent bucket, key) in scope `sc`, created on first touch.
+__device__ __forceinline__ uint32_t scope_lookup(uint32_t* overflow, const DevScope& sc, uint32_t parent, uint64_t key) {
+    if (sc.mode == SCOPE_DENSE) {
+        uint64_t rel = key - sc.dom_min;
+        if (key < sc.dom_min || rel >= sc.dom_size) return INVALID_BUCKET;
+        uint64_t idx = (uint64_t)parent * sc.dom_size + rel;
+        if (!sc.present[idx]) sc.present[idx] = 1;
+        return (uint32_t)idx;
+    }
+    uint64_t mask = sc.capacity - 1;
+    uint64_t h = hash_key(key, parent) & mask;
+    for (uint64_t probes = 0; probes <= mask;) {
+        uint32_t st = *((volatile uint32_t*)(sc.state + h));
+        if (st == ST_READY) {
+            if (*((volatile uint64_t*)(sc.keys + h)) == key && *((volatile uint32_t*)(sc.parents + h)) == parent)
+                return (uint32_t)h;
+            h = (h + 1) & mask;
+            probes++;
+            continue;
+        }
+        if (st == ST_EMPTY) {
+            // keep the load factor <= 3/4: beyond that report overflow and let the host grow the table
+            if (*((volatile unsigned long long*)sc.used) * 4ull >= sc.capacity * 3ull) break;
+            uint32_t old = atomicCAS(sc.state + h, (uint32_t)ST_EMPTY, (uint32_t)ST_BUSY);
+            if (old == ST_EMPTY) {
+                sc.keys[h] = key;
+                sc.parents[h] = parent;
+                __threadfence();
+                atomicExch(sc.state + h, (uint32_t)ST_READY);
+                atomicAdd(sc.used, 1ull);
+                return (uint32_t)h;
+            }
+        }
+        // BUSY (or lost the race): re-read the same slot
+    }
+    atomicExch(overflow, 1u);
+    return INVALID_BUCKET;
+}
+
+
 struct DevSlot {
     uint64_t* acc;   // per bucket of the enclosing scope.  MIN stores max(~code) so zero == empty identity
     uint8_t* seen;   // per bucket: Option is Some

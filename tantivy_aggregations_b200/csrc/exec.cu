@@ -400,6 +400,18 @@ static int alloc_percentile_buffers(ExecState& es) {
     return 0;
 }
 
+// every member of the plan's top tuple (below the leading filters) was handled by a fast-path launch
+static bool plan_fully_covered(const ExecState& es) {
+    const PlanMeta& m = *es.meta;
+    uint32_t node = 0;
+    while (node < m.nodes.size() && (m.nodes[node].op == TAGG_OP_FILTER || m.nodes[node].op == TAGG_OP_POST_FILTER)) node++;
+    if (node >= m.nodes.size()) return false;
+    if (m.nodes[node].op != TAGG_OP_TUPLE) return es.skip[node] != 0;
+    for (uint32_t c = node + 1; c < m.end[node]; c = m.end[c])
+        if (!es.skip[c]) return false;
+    return true;
+}
+
 static int build_dev_plan(ExecState& es) {
     const PlanMeta& m = *es.meta;
     DevPlan& P = es.hplan;
@@ -537,9 +549,16 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             handled = stream_try(es);
             if (handled < 0) return -handled;
         }
+        int mt = 0;
+        if (handled != 1 && ctx->path != 1) {  // K5: terms keyed by multi-valued / hashed fields
+            mt = mterms_try(es);
+            if (mt < 0) return -mt;
+            if (mt > 0 && plan_fully_covered(es)) handled = 1;
+            else if (mt > 0) handled = 2;
+        }
         if (handled != 1) {
             if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
-            es.path_used = handled == 2 ? 3 : 1;
+            es.path_used = mt > 0 ? 5 : handled == 2 ? 3 : 1;
             rc = build_dev_plan(es);
             if (rc) return rc;
             if (!es.uploads.empty())
@@ -549,7 +568,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
                 if (es.n_cand[i]) { ctx->launches++; es.n_launches++; }
             }
         } else {
-            es.path_used = 2;
+            es.path_used = mt > 0 ? 4 : 2;
         }
         CUDA_TRY(cudaEventRecord(es.ev1, es.st));
         lap("launched");

@@ -71,3 +71,5 @@ int comm_agree_domains(ExecState& es, std::vector<uint64_t>& dom);
 int comm_merge_arena(ExecState& es);
 // stream.cu: returns 1 if a streaming fast shape handled the plan, 0 if not applicable, <0 = -status
 int stream_try(ExecState& es);
+// mterms.cu: terms keyed by a multi-valued field / hashed key domain; returns members handled, <0 = -status
+int mterms_try(ExecState& es);

@@ -6,52 +6,6 @@
 #include "dev.cuh"
 #include "host.h"
 
-#define INVALID_BUCKET 0xFFFFFFFFu
-
-__device__ __forceinline__ uint64_t hash_key(uint64_t key, uint32_t parent) {
-    return mix64(key ^ ((uint64_t)parent * 0x9E3779B97F4A7C15ull));
-}
-
-// `entry(key).or_insert_with(create_fruit)` (terms.rs:129-130, histogram.rs:148-149):
-// bucket index of (parent bucket, key) in scope `sc`, created on first touch.
-__device__ uint32_t scope_lookup(const DevPlan* P, const DevScope& sc, uint32_t parent, uint64_t key) {
-    if (sc.mode == SCOPE_DENSE) {
-        uint64_t rel = key - sc.dom_min;
-        if (key < sc.dom_min || rel >= sc.dom_size) return INVALID_BUCKET;
-        uint64_t idx = (uint64_t)parent * sc.dom_size + rel;
-        if (!sc.present[idx]) sc.present[idx] = 1;
-        return (uint32_t)idx;
-    }
-    uint64_t mask = sc.capacity - 1;
-    uint64_t h = hash_key(key, parent) & mask;
-    for (uint64_t probes = 0; probes <= mask;) {
-        uint32_t st = *((volatile uint32_t*)(sc.state + h));
-        if (st == ST_READY) {
-            if (*((volatile uint64_t*)(sc.keys + h)) == key && *((volatile uint32_t*)(sc.parents + h)) == parent)
-                return (uint32_t)h;
-            h = (h + 1) & mask;
-            probes++;
-            continue;
-        }
-        if (st == ST_EMPTY) {
-            // keep the load factor <= 3/4: beyond that report overflow and let the host grow the table
-            if (*((volatile unsigned long long*)sc.used) * 4ull >= sc.capacity * 3ull) break;
-            uint32_t old = atomicCAS(sc.state + h, (uint32_t)ST_EMPTY, (uint32_t)ST_BUSY);
-            if (old == ST_EMPTY) {
-                sc.keys[h] = key;
-                sc.parents[h] = parent;
-                __threadfence();
-                atomicExch(sc.state + h, (uint32_t)ST_READY);
-                atomicAdd(sc.used, 1ull);
-                return (uint32_t)h;
-            }
-        }
-        // BUSY (or lost the race): re-read the same slot
-    }
-    atomicExch(P->overflow, 1u);
-    return INVALID_BUCKET;
-}
-
 __device__ __forceinline__ bool pred_test(const DevNode& nd, uint64_t code) {
     if (nd.pred == TAGG_PRED_RANGE) return code >= nd.u0 && code <= nd.u1;
     if (nd.pred == TAGG_PRED_LUT) {
@@ -138,7 +92,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                     const DevNode& nd = P->nodes[f.node];
                     uint32_t b = INVALID_BUCKET;
                     while (++f.cur < f.stop) {
-                        b = scope_lookup(P, P->scopes[nd.own_scope], f.saved_bucket, col_get(S.cols[nd.col + 1], f.cur));
+                        b = scope_lookup(P->overflow, P->scopes[nd.own_scope], f.saved_bucket, col_get(S.cols[nd.col + 1], f.cur));
                         if (b != INVALID_BUCKET) break;
                     }
                     if (b != INVALID_BUCKET) {
@@ -201,7 +155,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                 }
                 case TAGG_OP_TERMS: {
                     if (!nd.multi) {  // terms.rs:127-132
-                        uint32_t b = scope_lookup(P, P->scopes[nd.own_scope], bucket, col_get(S.cols[nd.col], doc));
+                        uint32_t b = scope_lookup(P->overflow, P->scopes[nd.own_scope], bucket, col_get(S.cols[nd.col], doc));
                         if (b == INVALID_BUCKET || sp >= TAGG_MAX_DEPTH) { pc = nd.end; break; }
                         Frame& f = frames[sp++];
                         f.end = nd.end; f.body = pc + 1; f.node = pc; f.is_loop = 0; f.saved_bucket = bucket;
@@ -212,7 +166,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                         uint32_t b = INVALID_BUCKET;
                         uint64_t cur = a;
                         for (; cur < e; cur++) {
-                            b = scope_lookup(P, P->scopes[nd.own_scope], bucket, col_get(S.cols[nd.col + 1], cur));
+                            b = scope_lookup(P->overflow, P->scopes[nd.own_scope], bucket, col_get(S.cols[nd.col + 1], cur));
                             if (b != INVALID_BUCKET) break;
                         }
                         if (b == INVALID_BUCKET || sp >= TAGG_MAX_DEPTH) { pc = nd.end; break; }
@@ -227,7 +181,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                 case TAGG_OP_HISTOGRAM: {  // histogram.rs:136-152
                     uint64_t ord;
                     if (!hist_ord(col_get(S.cols[nd.col], doc), nd.f0, nd.f1, &ord)) { pc = nd.end; break; }
-                    uint32_t b = scope_lookup(P, P->scopes[nd.own_scope], bucket, ord);
+                    uint32_t b = scope_lookup(P->overflow, P->scopes[nd.own_scope], bucket, ord);
                     if (b == INVALID_BUCKET || sp >= TAGG_MAX_DEPTH) { pc = nd.end; break; }
                     Frame& f = frames[sp++];
                     f.end = nd.end; f.body = pc + 1; f.node = pc; f.is_loop = 0; f.saved_bucket = bucket;
