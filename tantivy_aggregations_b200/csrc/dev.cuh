@@ -161,7 +161,19 @@ __device__ __forceinline__ uint32_t scope_lookup(uint32_t* overflow, const DevSc
     }
     uint64_t mask = sc.capacity - 1;
     uint64_t h = hash_key(key, parent) & mask;
+    const bool root = sc.parent == 0;  // buckets of a top-level scope all hang off parent bucket 0
     for (uint64_t probes = 0; probes <= mask;) {
+        // fast pre-check on the key cell alone (a key, once written, never changes; an all-zero cell is
+        // ambiguous — empty or key 0 — and takes the state-checked path below)
+        if (root) {
+            const uint64_t k = __ldcg(sc.keys + h);
+            if (k != 0) {
+                if (k == key) return (uint32_t)h;
+                h = (h + 1) & mask;
+                probes++;
+                continue;
+            }
+        }
         uint32_t st = *((volatile uint32_t*)(sc.state + h));
         if (st == ST_READY) {
             if (*((volatile uint64_t*)(sc.keys + h)) == key && *((volatile uint32_t*)(sc.parents + h)) == parent)

@@ -31,8 +31,21 @@
 #define MT_MAXPRED 4
 #define MT_MAXCOUNTS 2
 #define MT_U 4           // key occurrences in flight per thread
+#define MT_DU (MT_TILE / MT_SUB_THREADS)  // documents per thread in the doc phase
 
 enum { MO_SUM = 1, MO_MIN = 2, MO_MAX = 4 };
+// Option flags ("the leaf saw a value in this bucket", sum.rs:97-101 / minmax.rs:99-105) without a scattered
+// global access per occurrence:
+//   SEEN_BUCKET   single-valued leaf: Some exactly where the bucket exists (aliased to the bucket-existence flags)
+//   SEEN_DERIVED  read off an accumulator after the pass (k_mterms_fixup): a min / max cell that left its identity,
+//                 or an f64 sum cell that left -0.0 (the cells start at -0.0: x + -0.0 == x for every x, and only
+//                 contributions that ARE the identity need an explicit flag store)
+//   SEEN_EXPLICIT check-and-set per occurrence (integer sums only: every bit pattern is a legitimate sum)
+enum { SEEN_BUCKET = 0, SEEN_DERIVED = 1, SEEN_EXPLICIT = 2 };
+// bucket existence: from the bucket counts after the pass | CTA bitmap in shared memory flushed at the end |
+// check-and-set per occurrence (the bitmap does not fit) | the hash table's own slot states
+enum { PRESENT_COUNTS = 0, PRESENT_BITMAP = 1, PRESENT_EXPLICIT = 2, PRESENT_HASH = 3 };
+#define NEG_ZERO_BITS 0x8000000000000000ull
 enum { MP_FILTER = 0, MP_RANGE = 1, MP_LUT = 2, MP_RANGE_ANY = 3, MP_LUT_ANY = 4 };
 
 struct MGroup {
@@ -40,6 +53,8 @@ struct MGroup {
     uint32_t kind, multi, ops;
     uint64_t *acc_sum, *acc_min, *acc_max;
     uint8_t* seen;    // Option flags of the group's slots (one array, aliased by all of them)
+    uint32_t seen_mode;   // SEEN_*: how the Option flags of this group are produced
+    uint32_t derive_op;   // SEEN_DERIVED: the op whose accumulator tells (MO_MIN / MO_MAX: cell != 0; MO_SUM f64: cell != -0.0)
     uint32_t soff_sum, soff_min, soff_max;  // per-document folded contribution, offsets inside a sub-block's shared block
 };
 struct MPred {
@@ -60,10 +75,10 @@ struct MParams {
     uint64_t* count_acc[MT_MAXCOUNTS];
     int32_t n_groups;
     MGroup groups[MT_MAXGROUPS];
-    uint32_t full_mask;      // flag bits of a document that contributes to every group
-    uint32_t bitmap_bytes;   // CTA-private "bucket fully flagged" bitmap (dense scopes), 0 = none
+    uint32_t present_mode;   // PRESENT_*
+    uint32_t bitmap_bytes;   // PRESENT_BITMAP: CTA-private bucket-existence bitmap in shared memory
     uint32_t sub_bytes;      // shared bytes per sub-block
-    uint32_t soff_koff, soff_docof, soff_flags;
+    uint32_t soff_koff, soff_docof, soff_flags, soff_cols;
 };
 
 __device__ __forceinline__ bool mpred_value(const MPred& pr, uint64_t code) {
@@ -75,22 +90,43 @@ __device__ __forceinline__ bool mpred_value(const MPred& pr, uint64_t code) {
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// the key column of the current segment, held in registers; both words of a value are always fetched (the
-// allocation is padded, dev.cuh), so the two loads are independent and there is no branch on the straddle
-struct KeyCol {
+// Column descriptors of the current segment, cached in the sub-block's shared memory (slot 0: key offsets,
+// 1: key values, 2 + 2g / 3 + 2g: offsets / values of leaf group g).  Both words of a value are always
+// fetched (the allocation is padded, dev.cuh), so the two loads are independent and nothing branches on
+// the straddle.
+struct ColS {
     const uint64_t* words;
     uint64_t minv, mask;
-    uint32_t nb;
+    uint32_t nb, pad;
 };
-__device__ __forceinline__ uint64_t key_get(const KeyCol& c, uint64_t i) {
+#define MT_NCOLS (2 + 2 * MT_MAXGROUPS)
+__device__ __forceinline__ uint64_t cget(const ColS& c, uint64_t i) {
     const uint64_t bit = i * c.nb;
+    if (c.nb <= 32) {  // narrow columns (keys, offsets): 32-bit words and one funnel shift
+        const uint32_t* w32 = (const uint32_t*)c.words + (bit >> 5);
+        const uint32_t lo = __ldg(w32), hi = __ldg(w32 + 1);
+        return (uint64_t)(__funnelshift_r(lo, hi, (uint32_t)bit & 31u) & (uint32_t)c.mask) + c.minv;
+    }
     const uint64_t w = bit >> 6;
     const uint32_t sh = (uint32_t)bit & 63u;
     const uint64_t lo = __ldg(c.words + w), hi = __ldg(c.words + w + 1);
     const uint64_t v = (lo >> sh) | ((hi << 1) << (63u - sh));
     return (v & c.mask) + c.minv;
 }
+// ask L2 for the packed bytes of values [lo, hi) of a column (the sub-block's next tile)
+__device__ __forceinline__ void l2_prefetch_values(const ColS& c, uint64_t lo, uint64_t hi) {
+    if (hi <= lo || c.nb == 0) return;
+    const uint64_t b0 = (lo * c.nb) >> 3, b1 = (hi * c.nb + 7) >> 3;
+    const uint8_t* p0 = (const uint8_t*)c.words + (b0 & ~(uint64_t)15);
+    uint64_t bytes = (b1 - (b0 & ~(uint64_t)15) + 15) & ~(uint64_t)15;
+    if (bytes > (1u << 20)) bytes = 1u << 20;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((uint32_t)bytes) : "memory");
+}
+__device__ __forceinline__ void cols_load(ColS* dst, const DevColumn& c) {
+    dst->words = c.words; dst->minv = c.min_value; dst->mask = c.mask; dst->nb = c.num_bits; dst->pad = 0;
+}
 
+template <bool DENSE, int NG, int NC>
 __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const __grid_constant__ MParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, sub = tid / MT_SUB_THREADS, st = tid % MT_SUB_THREADS;
@@ -100,75 +136,135 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
     uint32_t* koff = (uint32_t*)(base + p.soff_koff);    // MT_TILE + 1 key offsets relative to the tile's first key
     uint16_t* docof = (uint16_t*)(base + p.soff_docof);  // MT_CHUNK tile-local document indices
     uint8_t* flags = base + p.soff_flags;                // per document: bit 0 matched, bit 1 + g contributes to group g
-    if (p.bitmap_bytes) {
+    ColS* cs = (ColS*)(base + p.soff_cols);
+    const bool has_bitmap = DENSE && p.present_mode == PRESENT_BITMAP;
+    if (has_bitmap) {
         for (uint32_t i = tid; i < p.bitmap_bytes / 4; i += blockDim.x) bitmap[i] = 0;
         __syncthreads();
     }
-    const bool dense = p.scope.mode == SCOPE_DENSE;
-    uint32_t cur_seg = 0;
+    uint32_t cur_seg = 0xffffffffu, seg = 0;
+    const uint64_t dom_min = p.scope.dom_min, dom_size = p.scope.dom_size;
 
     for (uint64_t tile = (uint64_t)blockIdx.x * n_sub + sub; tile < p.n_tiles; tile += (uint64_t)gridDim.x * n_sub) {
-        while (cur_seg + 1 < p.n_segs && __ldg(p.tile_begin + cur_seg + 1) <= (uint32_t)tile) cur_seg++;
-        const DevSegment& S = p.segs[cur_seg];
-        const uint32_t d0 = ((uint32_t)tile - __ldg(p.tile_begin + cur_seg)) * MT_TILE;
-        const uint32_t max_doc = S.max_doc;
-        const uint32_t nd = min((uint32_t)MT_TILE, max_doc - d0);
-        const DevColumn& kidx = S.cols[p.key_col];
-        KeyCol kc;
+        while (seg + 1 < p.n_segs && __ldg(p.tile_begin + seg + 1) <= (uint32_t)tile) seg++;
+        const DevSegment& S = p.segs[seg];
+        if (seg != cur_seg) {  // uniform over the sub-block: refresh the cached column descriptors
+            named_bar(1 + sub, MT_SUB_THREADS);
+            if (st == 0) cols_load(cs + 0, S.cols[p.key_col]);
+            if (st == 1) cols_load(cs + 1, S.cols[p.key_multi ? p.key_col + 1 : p.key_col]);
+            if (st >= 2 && st < 2 + 2 * NG) {
+                const MGroup& G = p.groups[(st - 2) >> 1];
+                cols_load(cs + st, S.cols[G.multi ? G.col + ((st - 2) & 1) : G.col]);
+            }
+            named_bar(1 + sub, MT_SUB_THREADS);
+            cur_seg = seg;
+        }
+        const uint32_t d0 = ((uint32_t)tile - __ldg(p.tile_begin + seg)) * MT_TILE;
+        const uint32_t nd = min((uint32_t)MT_TILE, S.max_doc - d0);
+        const uint64_t kbase = p.key_multi ? cget(cs[0], d0) : (uint64_t)d0;
+        const bool plain = S.main.kind == DS_ALL && !S.has_deletes && p.n_preds == 0;
+        // ---- L2 prefetch of the sub-block's NEXT tile: fixed-position slices (offset columns) now, the
+        //      value slices (whose position depends on the offsets at the tile's ends) after the doc phase
+        const uint64_t ntile = tile + (uint64_t)gridDim.x * n_sub;
+        uint64_t pf_lo = 0, pf_hi = 0;  // lanes 1 / 3 + 2g of warp 0: value range of the next tile
+        int pf_col = -1;
+        if (st < 2 + 2 * NG && ntile < p.n_tiles && ntile < __ldg(p.tile_begin + seg + 1)) {
+            const uint32_t nd0 = ((uint32_t)ntile - __ldg(p.tile_begin + seg)) * MT_TILE;
+            const uint32_t nnd = min((uint32_t)MT_TILE, S.max_doc - nd0);
+            const bool is_vals = st & 1;
+            const bool multi = st < 2 ? p.key_multi != 0 : p.groups[(st - 2) >> 1].multi != 0;
+            if (!is_vals) {
+                if (multi) l2_prefetch_values(cs[st], nd0, (uint64_t)nd0 + nnd + 1);
+            } else {
+                pf_col = (int)st;
+                if (multi) { pf_lo = cget(cs[st - 1], nd0); pf_hi = cget(cs[st - 1], (uint64_t)nd0 + nnd); }
+                else { pf_lo = nd0; pf_hi = (uint64_t)nd0 + nnd; }
+            }
+        }
+        // ---- doc phase: MT_DU documents per thread in flight --------------------------------------------
         {
-            const DevColumn& kv = S.cols[p.key_multi ? p.key_col + 1 : p.key_col];
-            kc.words = kv.words; kc.minv = kv.min_value; kc.mask = kv.mask; kc.nb = kv.num_bits;
-        }
-        const uint64_t kbase = p.key_multi ? col_get(kidx, d0) : (uint64_t)d0;
-        // ---- doc phase ---------------------------------------------------------------------------------
-        for (uint32_t i = st; i <= nd; i += MT_SUB_THREADS) {
-            const uint32_t doc = d0 + i;
-            koff[i] = p.key_multi ? (uint32_t)(col_get(kidx, doc) - kbase) : i;
-            if (i == nd) break;
-            bool ok = docset_test(S, S.main, doc);
-            if (ok && S.has_deletes) ok = !((S.deleted[doc >> 5] >> (doc & 31)) & 1u);  // searcher.rs:41-46
-            for (int k = 0; ok && k < p.n_preds; k++) {
-                const MPred& pr = p.preds[k];
-                if (pr.type == MP_FILTER) {  // filter.rs:100-122
-                    ok = docset_test(S, S.filters[pr.filter], doc);
-                } else if (pr.type == MP_RANGE || pr.type == MP_LUT) {  // post_filter.rs:245-249
-                    ok = mpred_value(pr, col_get(S.cols[pr.col], doc));
-                } else {  // post_filter.rs:289-297: any value passes
-                    uint64_t a = col_get(S.cols[pr.col], doc), e = col_get(S.cols[pr.col], (uint64_t)doc + 1);
-                    bool any = false;
-                    for (uint64_t j = a; j < e && !any; j++) any = mpred_value(pr, col_get(S.cols[pr.col + 1], j));
-                    ok = any;
-                }
-            }
-            uint32_t f = ok ? 1u : 0u;
-            if (ok) {
+            uint32_t di_[MT_DU], fl[MT_DU];
+            uint64_t ga[MT_DU][NG ? NG : 1], ge[MT_DU][NG ? NG : 1];
 #pragma unroll
-                for (int g = 0; g < MT_MAXGROUPS; g++) {
-                    if (g >= p.n_groups) break;
-                    const MGroup& G = p.groups[g];
-                    uint64_t a = doc, e = (uint64_t)doc + 1;
-                    if (G.multi) { a = col_get(S.cols[G.col], doc); e = col_get(S.cols[G.col], (uint64_t)doc + 1); }
-                    const DevColumn& vc = S.cols[G.multi ? G.col + 1 : G.col];
-                    uint64_t sum = 0, mn = 0, mx = 0;  // min in max-form (~code), like the arena
-                    for (uint64_t j = a; j < e; j++) {
-                        uint64_t code = col_get(vc, j);
-                        if (G.ops & MO_SUM) {
-                            if (G.kind == TAGG_F64) sum = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)sum), code_to_f64(code)));
-                            else sum += code_to_bits(G.kind, code);
+            for (int u = 0; u < MT_DU; u++) {
+                const uint32_t i = st + u * MT_SUB_THREADS;
+                di_[u] = i;
+                fl[u] = 0;
+                if (i < nd) koff[i] = p.key_multi ? (uint32_t)(cget(cs[0], d0 + i) - kbase) : i;
+                if (u == 0 && st == 0) koff[nd] = p.key_multi ? (uint32_t)(cget(cs[0], (uint64_t)d0 + nd) - kbase) : nd;
+                if (i >= nd) continue;
+                const uint32_t doc = d0 + i;
+                bool ok = true;
+                if (!plain) {
+                    ok = docset_test(S, S.main, doc);
+                    if (ok && S.has_deletes) ok = !((S.deleted[doc >> 5] >> (doc & 31)) & 1u);  // searcher.rs:41-46
+                    for (int k = 0; ok && k < p.n_preds; k++) {
+                        const MPred& pr = p.preds[k];
+                        if (pr.type == MP_FILTER) {  // filter.rs:100-122
+                            ok = docset_test(S, S.filters[pr.filter], doc);
+                        } else if (pr.type == MP_RANGE || pr.type == MP_LUT) {  // post_filter.rs:245-249
+                            ok = mpred_value(pr, col_get(S.cols[pr.col], doc));
+                        } else {  // post_filter.rs:289-297: any value passes
+                            uint64_t a = col_get(S.cols[pr.col], doc), e = col_get(S.cols[pr.col], (uint64_t)doc + 1);
+                            bool any = false;
+                            for (uint64_t j = a; j < e && !any; j++) any = mpred_value(pr, col_get(S.cols[pr.col + 1], j));
+                            ok = any;
                         }
-                        mn = max(mn, ~code);
-                        mx = max(mx, code);
                     }
-                    if (e > a) {
-                        f |= 2u << g;
-                        if (G.ops & MO_SUM) ((uint64_t*)(base + G.soff_sum))[i] = sum;
-                        if (G.ops & MO_MIN) ((uint64_t*)(base + G.soff_min))[i] = mn;
-                        if (G.ops & MO_MAX) ((uint64_t*)(base + G.soff_max))[i] = mx;
+                }
+                fl[u] = ok ? 1u : 0u;
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    ga[u][g] = doc; ge[u][g] = ok ? (uint64_t)doc + 1 : doc;
+                    if (p.groups[g].multi) {
+                        ga[u][g] = cget(cs[2 + 2 * g], doc);
+                        ge[u][g] = ok ? cget(cs[2 + 2 * g], (uint64_t)doc + 1) : ga[u][g];
                     }
                 }
             }
-            flags[i] = (uint8_t)f;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const MGroup& G = p.groups[g];
+                const ColS& vc = cs[3 + 2 * g];
+                uint64_t sum[MT_DU], mn[MT_DU], mx[MT_DU];  // min in max-form (~code), like the arena
+#pragma unroll
+                for (int u = 0; u < MT_DU; u++) { sum[u] = 0; mn[u] = 0; mx[u] = 0; }
+                for (uint64_t r = 0;; r++) {  // round r: the r-th value of each of the thread's documents
+                    uint64_t code[MT_DU];
+                    bool live[MT_DU], any = false;
+#pragma unroll
+                    for (int u = 0; u < MT_DU; u++) {
+                        live[u] = fl[u] && ga[u][g] + r < ge[u][g];
+                        code[u] = live[u] ? cget(vc, ga[u][g] + r) : 0;
+                        any = any || live[u];
+                    }
+                    if (!any) break;
+#pragma unroll
+                    for (int u = 0; u < MT_DU; u++) {
+                        if (!live[u]) continue;
+                        if (G.ops & MO_SUM) {
+                            if (G.kind == TAGG_F64) sum[u] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)sum[u]), code_to_f64(code[u])));
+                            else sum[u] += code_to_bits(G.kind, code[u]);
+                        }
+                        if (G.ops & MO_MIN) mn[u] = max(mn[u], ~code[u]);
+                        if (G.ops & MO_MAX) mx[u] = max(mx[u], code[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < MT_DU; u++) {
+                    if (fl[u] && ge[u][g] > ga[u][g]) {
+                        fl[u] |= 2u << g;
+                        if (G.ops & MO_SUM) ((uint64_t*)(base + G.soff_sum))[di_[u]] = sum[u];
+                        if (G.ops & MO_MIN) ((uint64_t*)(base + G.soff_min))[di_[u]] = mn[u];
+                        if (G.ops & MO_MAX) ((uint64_t*)(base + G.soff_max))[di_[u]] = mx[u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < MT_DU; u++)
+                if (di_[u] < nd) flags[di_[u]] = (uint8_t)fl[u];
         }
+        if (pf_col >= 0) l2_prefetch_values(cs[pf_col], pf_lo, pf_hi);
         named_bar(1 + sub, MT_SUB_THREADS);
         const uint32_t nk = koff[nd];
         for (uint32_t cbase = 0; cbase < nk; cbase += MT_CHUNK) {
@@ -185,59 +281,83 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                 uint64_t key[MT_U];
 #pragma unroll
                 for (int u = 0; u < MT_U; u++) {
-                    const uint32_t v = v0 + u * MT_SUB_THREADS;
-                    di[u] = 0; f[u] = 0;
-                    if (v < cn) { di[u] = docof[v]; f[u] = flags[di[u]]; }
+                    const uint32_t v = min(v0 + u * MT_SUB_THREADS, cn - 1);
+                    di[u] = docof[v];
+                    f[u] = v0 + u * MT_SUB_THREADS < cn ? flags[di[u]] : 0u;
+                    key[u] = cget(cs[1], kbase + cbase + v);
                 }
+                if (DENSE) {
 #pragma unroll
-                for (int u = 0; u < MT_U; u++) {
-                    key[u] = 0;
-                    if (f[u]) key[u] = key_get(kc, kbase + cbase + v0 + u * MT_SUB_THREADS);
-                }
-#pragma unroll
-                for (int u = 0; u < MT_U; u++) {
-                    b[u] = INVALID_BUCKET;
-                    if (!f[u]) continue;
-                    if (dense) {
-                        const uint64_t rel = key[u] - p.scope.dom_min;
-                        if (key[u] < p.scope.dom_min || rel >= p.scope.dom_size) { f[u] = 0; continue; }
-                        b[u] = (uint32_t)rel;
-                        // existence / Option flags: the CTA's bitmap remembers buckets whose flags are all set
-                        bool known = false;
-                        if (p.bitmap_bytes) known = (bitmap[b[u] >> 5] >> (b[u] & 31)) & 1u;
-                        if (!known) {
-                            if (!p.scope.present[b[u]]) p.scope.present[b[u]] = 1;
-                            for (int g = 0; g < p.n_groups; g++)
-                                if (((f[u] >> (1 + g)) & 1u) && p.groups[g].multi && !p.groups[g].seen[b[u]]) p.groups[g].seen[b[u]] = 1;
-                            if (p.bitmap_bytes && f[u] == p.full_mask) atomicOr(bitmap + (b[u] >> 5), 1u << (b[u] & 31));
+                    for (int u = 0; u < MT_U; u++) {
+                        const uint64_t rel = key[u] - dom_min;  // below the domain: wraps to a huge value
+                        if (rel >= dom_size) f[u] = 0;
+                        b[u] = f[u] ? (uint32_t)rel : 0u;
+                        if (p.present_mode == PRESENT_BITMAP) {
+                            if (f[u] && !((bitmap[b[u] >> 5] >> (b[u] & 31)) & 1u)) atomicOr(bitmap + (b[u] >> 5), 1u << (b[u] & 31));
+                        } else if (p.present_mode == PRESENT_EXPLICIT) {
+                            if (f[u] && !p.scope.present[b[u]]) p.scope.present[b[u]] = 1;
                         }
-                    } else {
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < MT_U; u++) {
+                        b[u] = 0;
+                        if (!f[u]) continue;
                         b[u] = scope_lookup(p.overflow, p.scope, 0, key[u]);
-                        if (b[u] == INVALID_BUCKET) { f[u] = 0; continue; }
-                        for (int g = 0; g < p.n_groups; g++)
-                            if (((f[u] >> (1 + g)) & 1u) && !p.groups[g].seen[b[u]]) p.groups[g].seen[b[u]] = 1;
+                        if (b[u] == INVALID_BUCKET) { f[u] = 0; b[u] = 0; }
+                    }
+                }
+                // Option flags that cannot be read off an accumulator afterwards
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const MGroup& G = p.groups[g];
+                    if (G.seen_mode == SEEN_EXPLICIT) {
+#pragma unroll
+                        for (int u = 0; u < MT_U; u++)
+                            if (((f[u] >> (1 + g)) & 1u) && !G.seen[b[u]]) G.seen[b[u]] = 1;
+                    } else if (G.seen_mode == SEEN_DERIVED) {  // a contribution equal to the identity leaves no trace in the cell
+                        const uint64_t* ss = (const uint64_t*)(base + (G.derive_op == MO_SUM ? G.soff_sum : G.derive_op == MO_MIN ? G.soff_min : G.soff_max));
+                        const uint64_t ident = G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull;
+#pragma unroll
+                        for (int u = 0; u < MT_U; u++)
+                            if (((f[u] >> (1 + g)) & 1u) && ss[di[u]] == ident) G.seen[b[u]] = 1;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < MT_U; u++) {
-                    if (!f[u]) continue;
-                    if (p.n_counts > 0) atomicAdd((unsigned long long*)(p.count_acc[0] + b[u]), 1ull);
-                    if (p.n_counts > 1) atomicAdd((unsigned long long*)(p.count_acc[1] + b[u]), 1ull);
+                    if (NC > 0 && f[u]) atomicAdd((unsigned long long*)(p.count_acc[0] + b[u]), 1ull);
+                    if (NC > 1 && f[u]) atomicAdd((unsigned long long*)(p.count_acc[1] + b[u]), 1ull);
+                }
 #pragma unroll
-                    for (int g = 0; g < MT_MAXGROUPS; g++) {
-                        if (g >= p.n_groups || !((f[u] >> (1 + g)) & 1u)) continue;
-                        const MGroup& G = p.groups[g];
-                        if (G.ops & MO_SUM) {
-                            const uint64_t s = ((const uint64_t*)(base + G.soff_sum))[di[u]];
-                            if (G.kind == TAGG_F64) atomicAdd((double*)(G.acc_sum + b[u]), __longlong_as_double((long long)s));
-                            else atomicAdd((unsigned long long*)(G.acc_sum + b[u]), (unsigned long long)s);
+                for (int g = 0; g < NG; g++) {
+                    const MGroup& G = p.groups[g];
+                    if (G.ops & MO_SUM) {
+                        const uint64_t* ss = (const uint64_t*)(base + G.soff_sum);
+                        if (G.kind == TAGG_F64) {
+#pragma unroll
+                            for (int u = 0; u < MT_U; u++)
+                                if ((f[u] >> (1 + g)) & 1u) atomicAdd((double*)(G.acc_sum + b[u]), __longlong_as_double((long long)ss[di[u]]));
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < MT_U; u++)
+                                if ((f[u] >> (1 + g)) & 1u) atomicAdd((unsigned long long*)(G.acc_sum + b[u]), (unsigned long long)ss[di[u]]);
                         }
-                        if (G.ops & MO_MIN) {
-                            const uint64_t m = ((const uint64_t*)(base + G.soff_min))[di[u]];
+                    }
+                    if (G.ops & MO_MIN) {
+                        const uint64_t* ss = (const uint64_t*)(base + G.soff_min);
+#pragma unroll
+                        for (int u = 0; u < MT_U; u++) {
+                            if (!((f[u] >> (1 + g)) & 1u)) continue;
+                            const uint64_t m = ss[di[u]];
                             if (G.acc_min[b[u]] < m && __ldcg(G.acc_min + b[u]) < m) atomicMax((unsigned long long*)(G.acc_min + b[u]), (unsigned long long)m);
                         }
-                        if (G.ops & MO_MAX) {
-                            const uint64_t m = ((const uint64_t*)(base + G.soff_max))[di[u]];
+                    }
+                    if (G.ops & MO_MAX) {
+                        const uint64_t* ss = (const uint64_t*)(base + G.soff_max);
+#pragma unroll
+                        for (int u = 0; u < MT_U; u++) {
+                            if (!((f[u] >> (1 + g)) & 1u)) continue;
+                            const uint64_t m = ss[di[u]];
                             if (G.acc_max[b[u]] < m && __ldcg(G.acc_max + b[u]) < m) atomicMax((unsigned long long*)(G.acc_max + b[u]), (unsigned long long)m);
                         }
                     }
@@ -245,6 +365,57 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             }
             named_bar(1 + sub, MT_SUB_THREADS);
         }
+    }
+    if (has_bitmap) {  // bucket existence, written once per CTA with coalesced stores
+        __syncthreads();
+        for (uint32_t i = tid; i < (uint32_t)dom_size; i += blockDim.x)
+            if ((bitmap[i >> 5] >> (i & 31)) & 1u) p.scope.present[i] = 1;
+    }
+}
+
+// before the pass: f64 sum cells whose Option flags are derived start at -0.0
+__global__ void k_mterms_init(uint64_t* __restrict__ acc, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc[i] = NEG_ZERO_BITS;
+}
+// after the pass: Option flags from the accumulators, untouched -0.0 cells back to the arena's zero identity,
+// bucket existence from the counts
+struct MFix {
+    uint64_t n;
+    uint8_t* present;
+    const uint64_t* counts;  // non-null: present[b] = counts[b] != 0
+    int32_t n_groups;
+    struct { uint64_t* cell; uint8_t* seen; uint32_t derive_op; uint32_t pad; } g[MT_MAXGROUPS];
+};
+__global__ void k_mterms_fixup(const MFix x) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < x.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (x.counts) x.present[i] = x.counts[i] != 0;
+        for (int g = 0; g < x.n_groups; g++) {
+            const uint64_t v = x.g[g].cell[i];
+            if (x.g[g].derive_op == MO_SUM) {
+                if (v != NEG_ZERO_BITS) x.g[g].seen[i] = 1;
+                else if (!x.g[g].seen[i]) x.g[g].cell[i] = 0;
+            } else if (v != 0) {
+                x.g[g].seen[i] = 1;
+            }
+        }
+    }
+}
+
+typedef void (*mterms_fn)(const MParams);
+template <bool DENSE, int NG>
+static mterms_fn pick_nc(int nc) {
+    switch (nc) {
+        case 0: return (mterms_fn)k_mterms<DENSE, NG, 0>;
+        case 1: return (mterms_fn)k_mterms<DENSE, NG, 1>;
+        default: return (mterms_fn)k_mterms<DENSE, NG, 2>;
+    }
+}
+template <bool DENSE>
+static mterms_fn pick_ng(int ng, int nc) {
+    switch (ng) {
+        case 0: return pick_nc<DENSE, 0>(nc);
+        case 1: return pick_nc<DENSE, 1>(nc);
+        default: return pick_nc<DENSE, 2>(nc);
     }
 }
 
@@ -355,9 +526,17 @@ int mterms_try(ExecState& es) {
             else if (group_seen[a.second] == (size_t)-1) group_seen[a.second] = SL.off_seen;
             else SL.off_seen = group_seen[a.second];
         }
-        for (int g = 0; g < p.n_groups; g++)
-            p.groups[g].seen = es.arena + (group_seen[g] == (size_t)-1 ? L.off_present : group_seen[g]);
-
+        for (int g = 0; g < p.n_groups; g++) {
+            MGroup& G = p.groups[g];
+            if (group_seen[g] == (size_t)-1) {
+                G.seen = es.arena + L.off_present;
+                G.seen_mode = SEEN_BUCKET;
+            } else {
+                G.seen = es.arena + group_seen[g];
+                G.derive_op = (G.ops & MO_MIN) ? MO_MIN : (G.ops & MO_MAX) ? MO_MAX : (G.kind == TAGG_F64 ? MO_SUM : 0);
+                G.seen_mode = G.derive_op ? SEEN_DERIVED : SEEN_EXPLICIT;
+            }
+        }
         p.key_col = m.col_slot[mem];
         p.key_multi = nd.multi ? 1 : 0;
         p.scope.mode = L.mode;
@@ -374,14 +553,13 @@ int mterms_try(ExecState& es) {
             p.scope.used = (unsigned long long*)(es.arena + L.off_used);
         }
         p.overflow = (uint32_t*)(es.arena + es.off_overflow);
-        p.full_mask = 1u;
-        for (int g = 0; g < p.n_groups; g++) p.full_mask |= 2u << g;
 
         // shared-memory plan
         uint32_t off = 0;
         p.soff_koff = off; off += (MT_TILE + 1) * 4; off = (off + 15) & ~15u;
         p.soff_docof = off; off += MT_CHUNK * 2;
         p.soff_flags = off; off += MT_TILE; off = (off + 15) & ~15u;
+        p.soff_cols = off; off += MT_NCOLS * (uint32_t)sizeof(ColS);
         for (int g = 0; g < p.n_groups; g++) {
             MGroup& G = p.groups[g];
             if (G.ops & MO_SUM) { G.soff_sum = off; off += MT_TILE * 8; }
@@ -391,26 +569,42 @@ int mterms_try(ExecState& es) {
         p.sub_bytes = off;
         const size_t SMEM_MAX = 225 * 1024;
         p.bitmap_bytes = 0;
-        if (dense) {
+        p.present_mode = dense ? (p.n_counts > 0 ? PRESENT_COUNTS : PRESENT_EXPLICIT) : PRESENT_HASH;
+        if (p.present_mode == PRESENT_EXPLICIT) {
             size_t bb = (((size_t)L.dom_size + 31) / 32) * 4;
             bb = (bb + 15) & ~(size_t)15;
-            if (bb + 2 * (size_t)p.sub_bytes <= SMEM_MAX) p.bitmap_bytes = (uint32_t)bb;
+            if (bb + 2 * (size_t)p.sub_bytes <= SMEM_MAX) { p.bitmap_bytes = (uint32_t)bb; p.present_mode = PRESENT_BITMAP; }
         }
         uint32_t n_sub = (uint32_t)std::min<size_t>(MT_MAXSUB, (SMEM_MAX - p.bitmap_bytes) / p.sub_bytes);
         if (n_sub < 1) continue;
         const size_t smem_bytes = p.bitmap_bytes + (size_t)n_sub * p.sub_bytes;
-        static std::once_flag attr_once;
-        static cudaError_t attr_err = cudaSuccess;
-        std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute((const void*)k_mterms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); });
-        if (attr_err != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "cudaFuncSetAttribute(k_mterms) failed: %s", cudaGetErrorString(attr_err));
+        mterms_fn fn = dense ? pick_ng<true>(p.n_groups, p.n_counts) : pick_ng<false>(p.n_groups, p.n_counts);
+        {
+            static std::mutex attr_mu;
+            static std::vector<mterms_fn> attr_done;
+            std::lock_guard<std::mutex> g(attr_mu);
+            if (std::find(attr_done.begin(), attr_done.end(), fn) == attr_done.end()) {
+                if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX) != cudaSuccess)
+                    return -tagg_fail(TAGG_ERR_CUDA, "cudaFuncSetAttribute(k_mterms) failed: %s", cudaGetErrorString(cudaGetLastError()));
+                attr_done.push_back(fn);
+            }
+        }
         const int threads = (int)n_sub * MT_SUB_THREADS;
         int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_mterms, threads, smem_bytes) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, threads, smem_bytes) != cudaSuccess || per_sm < 1)
             return -tagg_fail(TAGG_ERR_CUDA, "k_mterms does not fit an SM (%zu bytes of shared memory)", smem_bytes);
 
         if (!es.uploads.empty())
             for (uint32_t c = 0; c < es.n_chunks; c++)
                 if (cudaStreamWaitEvent(es.st, es.call->chunk_ev[c], 0) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "stream ordering failed");
+        const uint64_t n_cells = L.capacity;
+        const unsigned aux_grid = (unsigned)std::min<uint64_t>((n_cells + 255) / 256, (uint64_t)es.ctx->sm_count * 8);
+        for (int g = 0; g < p.n_groups; g++)
+            if (p.groups[g].seen_mode == SEEN_DERIVED && p.groups[g].derive_op == MO_SUM) {
+                k_mterms_init<<<aux_grid, 256, 0, es.st>>>(p.groups[g].acc_sum, n_cells);
+                es.ctx->launches++;
+                es.n_launches++;
+            }
         {
             // one persistent launch over the tiles of every segment
             const size_t nseg = es.hsegs.size();
@@ -435,9 +629,30 @@ int mterms_try(ExecState& es) {
                 sp.n_tiles = (uint32_t)tiles;
                 const uint64_t units = (tiles + n_sub - 1) / n_sub;
                 const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, units);
-                k_mterms<<<grid, threads, smem_bytes, es.st>>>(sp);
+                fn<<<grid, threads, smem_bytes, es.st>>>(sp);
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_mterms launch failed: %s", cudaGetErrorString(e));
+                es.ctx->launches++;
+                es.n_launches++;
+            }
+        }
+        {
+            MFix fx;
+            memset(&fx, 0, sizeof(fx));
+            fx.n = n_cells;
+            if (p.present_mode == PRESENT_COUNTS) { fx.present = es.arena + L.off_present; fx.counts = p.count_acc[0]; }
+            for (int g = 0; g < p.n_groups; g++) {
+                const MGroup& G = p.groups[g];
+                if (G.seen_mode != SEEN_DERIVED) continue;
+                auto& d = fx.g[fx.n_groups++];
+                d.cell = G.derive_op == MO_SUM ? G.acc_sum : G.derive_op == MO_MIN ? G.acc_min : G.acc_max;
+                d.seen = G.seen;
+                d.derive_op = G.derive_op;
+            }
+            if (fx.counts || fx.n_groups) {
+                k_mterms_fixup<<<aux_grid, 256, 0, es.st>>>(fx);
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_mterms_fixup launch failed: %s", cudaGetErrorString(e));
                 es.ctx->launches++;
                 es.n_launches++;
             }
