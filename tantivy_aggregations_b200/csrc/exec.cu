@@ -31,6 +31,7 @@ const void* ExecState::pin(const void* src, size_t bytes) {
     return call->pinned + at;
 }
 void ExecState::free_temps() {
+    pct_rank_release(*this);
     for (void* p : temps) cudaFreeAsync(p, st);
     temps.clear();
     if (arena) cudaFreeAsync(arena, st);
@@ -386,6 +387,7 @@ static int alloc_percentile_buffers(ExecState& es) {
     const PlanMeta& m = *es.meta;
     // percentile materialisation: capacity = every value that could be inserted
     for (size_t k = 0; k < m.pct_node.size(); k++) {
+        if (es.rank[k].active) continue;  // handled by a streaming launch (pct.cu)
         const tagg_node& nd = m.nodes[m.pct_node[k]];
         uint64_t cap = 0;
         for (size_t i = 0; i < es.segs.size(); i++)
@@ -538,8 +540,6 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (rc) return rc;
         rc = layout_arena(es);
         if (rc) return rc;
-        rc = alloc_percentile_buffers(es);
-        if (rc) return rc;
         lap("layout");
 
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
@@ -559,6 +559,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (handled != 1) {
             if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
             es.path_used = mt > 0 ? 5 : handled == 2 ? 3 : 1;
+            rc = alloc_percentile_buffers(es);
+            if (rc) return rc;
             rc = build_dev_plan(es);
             if (rc) return rc;
             if (!es.uploads.empty())
@@ -591,11 +593,23 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         float ms = 0;
         cudaEventElapsedTime(&ms, es.ev0, es.ev1);
         ms_total += ms;
-        if (!overflow) break;
+        if (!overflow) {
+            bool redo = false;
+            for (int k = 0; k < 4 && !redo; k++)
+                if (es.rank[k].active) {
+                    rc = pct_rank_collect(es, k);
+                    if (rc < 0) return -rc;
+                    if (rc == 0) redo = true;
+                }
+            if (!redo) break;
+            overflow = 3;
+        }
+        if (overflow == 3) es.no_rank = true;  // the rank bins could not resolve this distribution: exact path
         if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
         if (attempt >= 6) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
         // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
-        es.hash_shift += 2;
+        if (overflow == 1) es.hash_shift += 2;
+        pct_rank_release(es);
         cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
         cudaFreeAsync(es.d_plan, es.st); es.d_plan = nullptr;
         for (int k = 0; k < 4; k++) {

@@ -43,6 +43,22 @@ struct ExecState {
     unsigned long long* pct_count[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t pct_cap[4] = {0, 0, 0, 0};
 
+    // percentiles on the streaming path (pct.cu): rank bins (count / min / max per equal-width code bin) between two
+    // thresholds chosen from a sample, exact lists outside them
+    struct RankState {
+        bool active = false;
+        uint64_t lo = 0, span = 0;   // binned codes: lo <= code < lo + span
+        uint32_t shift = 0, mul = 0, n_bins = 0;  // bin = umulhi((code - lo) >> shift, mul), or (code - lo) >> shift if mul == 0
+        uint8_t* d_block = nullptr;  // [tail counters 16 B][count u64 x n_bins][min][max][present u8 x n_bins]
+        uint64_t *d_count = nullptr, *d_min = nullptr, *d_max = nullptr;
+        uint8_t* d_present = nullptr;
+        unsigned long long* d_tail_count = nullptr;  // [0] appended values, [1] those below lo
+        uint64_t* d_tail = nullptr;
+        uint64_t tail_cap = 0;
+        PctSummary summary;          // filled by pct_rank_collect
+    } rank[4];
+    bool no_rank = false;            // a rank-bin pass failed its precision check: redo on the exact path
+
     uint64_t alg_bytes = 0;
     uint32_t n_launches = 0;
     uint32_t path_used = 0;
@@ -73,3 +89,8 @@ int comm_merge_arena(ExecState& es);
 int stream_try(ExecState& es);
 // mterms.cu: terms keyed by a multi-valued field / hashed key domain; returns members handled, <0 = -status
 int mterms_try(ExecState& es);
+// pct.cu: percentiles on the streaming path.  plan: 1 = rank-bin mode configured in es.rank[k], 0 = use the exact
+// path, <0 = -status.  collect (after the pass, synchronises): 1 = summary ready, 0 = precision check failed.
+int pct_rank_plan(ExecState& es, uint32_t node, int k);
+int pct_rank_collect(ExecState& es, int k);
+void pct_rank_release(ExecState& es);

@@ -22,13 +22,14 @@
 #include <algorithm>
 
 #include "exec.h"
+#include "narrow.cuh"
 
 #define MT_SUB_THREADS 256
 #define MT_MAXSUB 3
 #define MT_TILE 1024     // documents per sub-block tile
 #define MT_CHUNK 8192    // key occurrences expanded at a time
 #define MT_MAXGROUPS 2
-#define MT_MAXPRED 4
+#define MT_MAXPRED NARROW_MAXPRED
 #define MT_MAXCOUNTS 2
 #define MT_U 4           // key occurrences in flight per thread
 #define MT_DU (MT_TILE / MT_SUB_THREADS)  // documents per thread in the doc phase
@@ -46,7 +47,6 @@ enum { SEEN_BUCKET = 0, SEEN_DERIVED = 1, SEEN_EXPLICIT = 2 };
 // check-and-set per occurrence (the bitmap does not fit) | the hash table's own slot states
 enum { PRESENT_COUNTS = 0, PRESENT_BITMAP = 1, PRESENT_EXPLICIT = 2, PRESENT_HASH = 3 };
 #define NEG_ZERO_BITS 0x8000000000000000ull
-enum { MP_FILTER = 0, MP_RANGE = 1, MP_LUT = 2, MP_RANGE_ANY = 3, MP_LUT_ANY = 4 };
 
 struct MGroup {
     int32_t col;      // device column slot (multi: idx column, values at col + 1)
@@ -56,11 +56,6 @@ struct MGroup {
     uint32_t seen_mode;   // SEEN_*: how the Option flags of this group are produced
     uint32_t derive_op;   // SEEN_DERIVED: the op whose accumulator tells (MO_MIN / MO_MAX: cell != 0; MO_SUM f64: cell != -0.0)
     uint32_t soff_sum, soff_min, soff_max;  // per-document folded contribution, offsets inside a sub-block's shared block
-};
-struct MPred {
-    int32_t type, col, filter, pad;
-    uint64_t lo, hi;
-    const uint8_t* lut;
 };
 struct MParams {
     const DevSegment* segs;       // all segments of the call
@@ -80,13 +75,6 @@ struct MParams {
     uint32_t sub_bytes;      // shared bytes per sub-block
     uint32_t soff_koff, soff_docof, soff_flags, soff_cols;
 };
-
-__device__ __forceinline__ bool mpred_value(const MPred& pr, uint64_t code) {
-    if (pr.type == MP_RANGE || pr.type == MP_RANGE_ANY) return code >= pr.lo && code <= pr.hi;
-    if (code < pr.lo) return false;
-    uint64_t r = code - pr.lo;
-    return r < pr.hi && ((pr.lut[r >> 3] >> (r & 7)) & 1);
-}
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -194,24 +182,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                 if (u == 0 && st == 0) koff[nd] = p.key_multi ? (uint32_t)(cget(cs[0], (uint64_t)d0 + nd) - kbase) : nd;
                 if (i >= nd) continue;
                 const uint32_t doc = d0 + i;
-                bool ok = true;
-                if (!plain) {
-                    ok = docset_test(S, S.main, doc);
-                    if (ok && S.has_deletes) ok = !((S.deleted[doc >> 5] >> (doc & 31)) & 1u);  // searcher.rs:41-46
-                    for (int k = 0; ok && k < p.n_preds; k++) {
-                        const MPred& pr = p.preds[k];
-                        if (pr.type == MP_FILTER) {  // filter.rs:100-122
-                            ok = docset_test(S, S.filters[pr.filter], doc);
-                        } else if (pr.type == MP_RANGE || pr.type == MP_LUT) {  // post_filter.rs:245-249
-                            ok = mpred_value(pr, col_get(S.cols[pr.col], doc));
-                        } else {  // post_filter.rs:289-297: any value passes
-                            uint64_t a = col_get(S.cols[pr.col], doc), e = col_get(S.cols[pr.col], (uint64_t)doc + 1);
-                            bool any = false;
-                            for (uint64_t j = a; j < e && !any; j++) any = mpred_value(pr, col_get(S.cols[pr.col + 1], j));
-                            ok = any;
-                        }
-                    }
-                }
+                const bool ok = plain || doc_matches(S, p.preds, p.n_preds, doc);
                 fl[u] = ok ? 1u : 0u;
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
@@ -436,23 +407,7 @@ int mterms_try(ExecState& es) {
     MParams base;
     memset(&base, 0, sizeof(base));
     uint32_t node = 0;
-    while (node < n_nodes && (m.nodes[node].op == TAGG_OP_FILTER || m.nodes[node].op == TAGG_OP_POST_FILTER)) {
-        const tagg_node& nd = m.nodes[node];
-        if (base.n_preds >= MT_MAXPRED) return 0;
-        MPred& pr = base.preds[base.n_preds++];
-        if (nd.op == TAGG_OP_FILTER) {
-            pr.type = MP_FILTER;
-            pr.filter = (int32_t)nd.aux;
-        } else {
-            const bool lut = nd.pred == TAGG_PRED_LUT;
-            pr.type = nd.multi ? (lut ? MP_LUT_ANY : MP_RANGE_ANY) : (lut ? MP_LUT : MP_RANGE);
-            pr.col = m.col_slot[node];
-            pr.lo = nd.u0;
-            pr.hi = nd.u1;
-            pr.lut = lut ? es.plan->d_blobs[nd.aux] : nullptr;
-        }
-        node++;
-    }
+    if (!narrow_chain(es, base.preds, &base.n_preds, &node)) return 0;
     if (node >= n_nodes) return 0;
     std::vector<uint32_t> members;
     if (m.nodes[node].op == TAGG_OP_TUPLE) {

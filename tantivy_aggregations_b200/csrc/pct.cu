@@ -1,0 +1,291 @@
+// pct.cu — K4: percentiles_agg_f64 (percentile.rs:87-90, 163-177) on the streaming path.
+//
+// The reference inserts every matched value into a CKMS(eps = 0.01) sketch and answers percentile(q) with an element
+// whose rank is within +-eps*q*n of q*n.  Here the fruit is a list of EXACT order statistics (rank, value) dense
+// enough that every target rank has a stored neighbour well inside that band, produced in ONE pass over the column:
+//   1. k_pct_sample gathers ~64k matched values (a systematic sample of the doc stream); the host sorts them and
+//      picks two code thresholds lo < hi and a bin width 2^shift such that, going by the sample, every bin in
+//      [lo, hi) will hold fewer than eps/2 of the values below it;
+//   2. the streaming kernel (stream.cu, BK_RANK) keeps count / min / max per bin in shared memory — the minimum of
+//      a bin is the exact order statistic of rank (values below the bin) + 1, its maximum that of rank
+//      (values below) + count — and appends the few values outside [lo, hi) to an exact list;
+//   3. pct_rank_collect sorts the list, checks the precision bound on the real counts (count <= eps * values below,
+//      or a single distinct value) and emits the pairs.  If the check fails (a distribution the equal-width bins
+//      cannot resolve) the query is redone on the exact path (materialise + radix sort, generic.cu / result.cu).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "exec.h"
+#include "narrow.cuh"
+
+#define PCT_SAMPLE 65536u
+#define PCT_BINS 4096u
+#define PCT_MIN_DOCS (8ull << 20)  // below this the exact path is cheap enough
+#define PCT_EPS 0.01               // percentile.rs:174
+
+struct SampleParams {
+    const DevSegment* segs;
+    const uint64_t* doc_begin;  // n_segs + 1
+    uint32_t n_segs, n_samples;
+    uint64_t n_docs;
+    int32_t col, n_preds;
+    MPred preds[NARROW_MAXPRED];
+    uint64_t* out;
+    unsigned int* count;
+};
+
+__global__ void k_pct_sample(const SampleParams p) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n_samples) return;
+    // systematic sample: one document per stratum, at a hashed position inside it
+    const uint64_t stratum = p.n_docs / p.n_samples;
+    const uint64_t g = (uint64_t)s * stratum + mix64(s + 0x1234567ull) % stratum;
+    uint32_t lo = 0, hi = p.n_segs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (p.doc_begin[mid] <= g) lo = mid; else hi = mid;
+    }
+    const DevSegment& S = p.segs[lo];
+    const uint32_t doc = (uint32_t)(g - p.doc_begin[lo]);
+    if (doc >= S.max_doc || !doc_matches(S, p.preds, p.n_preds, doc)) return;
+    const uint64_t code = col_get(S.cols[p.col], doc);
+    p.out[atomicAdd(p.count, 1u)] = code;
+}
+
+__global__ void k_gather_u64(const uint64_t* __restrict__ src, const uint64_t* __restrict__ pos, uint64_t n, uint64_t* __restrict__ dst) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[pos[i]];
+}
+
+static inline uint64_t code_to_f64_bits(uint64_t c) { return (c >> 63) ? (c ^ 0x8000000000000000ull) : ~c; }
+
+void pct_rank_release(ExecState& es) {
+    for (auto& r : es.rank) {
+        if (r.d_block) cudaFreeAsync(r.d_block, es.st);
+        if (r.d_tail) cudaFreeAsync(r.d_tail, es.st);
+        r = ExecState::RankState();
+    }
+}
+
+int pct_rank_plan(ExecState& es, uint32_t node, int k) {
+    const PlanMeta& m = *es.meta;
+    if (es.no_rank || es.collective || k < 0 || k >= 4) return 0;
+    const size_t nseg = es.hsegs.size();
+    std::vector<uint64_t> begin(nseg + 1, 0);
+    for (size_t i = 0; i < nseg; i++) begin[i + 1] = begin[i] + es.hsegs[i].max_doc;
+    const uint64_t n_docs = begin[nseg];
+    if (n_docs < PCT_MIN_DOCS) return 0;
+
+    SampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    uint32_t first = 0;
+    if (!narrow_chain(es, sp.preds, &sp.n_preds, &first)) return 0;
+    sp.segs = es.d_segs;
+    sp.n_segs = (uint32_t)nseg;
+    sp.n_samples = PCT_SAMPLE;
+    sp.n_docs = n_docs;
+    sp.col = m.col_slot[node];
+
+    // host docsets must have landed before the sample looks at them
+    if (!es.uploads.empty())
+        for (uint32_t c = 0; c < es.n_chunks; c++)
+            if (cudaStreamWaitEvent(es.st, es.call->chunk_ev[c], 0) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "stream ordering failed");
+    uint8_t* d_tmp = nullptr;  // [doc_begin][count 16 B][sample][sorted sample][cub scratch]
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)PCT_SAMPLE, 0, 64, es.st);
+    const size_t off_begin = 0, off_count = (nseg + 1) * 8, off_sample = off_count + 16, off_sorted = off_sample + PCT_SAMPLE * 8,
+                 off_cub = off_sorted + PCT_SAMPLE * 8, total = off_cub + cub_bytes + 16;
+    if (cudaMallocAsync((void**)&d_tmp, total, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "percentile sample allocation failed");
+    es.temps.push_back(d_tmp);
+    if (cudaMemcpyAsync(d_tmp + off_begin, es.pin(begin.data(), (nseg + 1) * 8), (nseg + 1) * 8, cudaMemcpyHostToDevice, es.st) != cudaSuccess ||
+        cudaMemsetAsync(d_tmp + off_count, 0, 16, es.st) != cudaSuccess ||
+        cudaMemsetAsync(d_tmp + off_sample, 0xff, PCT_SAMPLE * 8, es.st) != cudaSuccess)  // empty slots sort to the end
+        return -tagg_fail(TAGG_ERR_CUDA, "percentile sample setup failed");
+    sp.doc_begin = (const uint64_t*)(d_tmp + off_begin);
+    sp.count = (unsigned int*)(d_tmp + off_count);
+    sp.out = (uint64_t*)(d_tmp + off_sample);
+    k_pct_sample<<<PCT_SAMPLE / 256, 256, 0, es.st>>>(sp);
+    es.ctx->launches++;
+    es.n_launches++;
+    if (cub::DeviceRadixSort::SortKeys(d_tmp + off_cub, cub_bytes, (const uint64_t*)(d_tmp + off_sample), (uint64_t*)(d_tmp + off_sorted),
+                                       (int)PCT_SAMPLE, 0, 64, es.st) != cudaSuccess)
+        return -tagg_fail(TAGG_ERR_CUDA, "percentile sample sort failed");
+    std::vector<uint64_t> smp(PCT_SAMPLE);
+    unsigned int mcount = 0;
+    if (cudaMemcpyAsync(smp.data(), d_tmp + off_sorted, PCT_SAMPLE * 8, cudaMemcpyDeviceToHost, es.st) != cudaSuccess ||
+        cudaMemcpyAsync(&mcount, d_tmp + off_count, 4, cudaMemcpyDeviceToHost, es.st) != cudaSuccess ||
+        cudaStreamSynchronize(es.st) != cudaSuccess)
+        return -tagg_fail(TAGG_ERR_CUDA, "percentile sample download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const uint64_t mm = std::min<uint64_t>(mcount, PCT_SAMPLE);
+    if (mm < 8192) return 0;  // a selective query: few values, the exact path sorts them cheaply
+    const double n_est = (double)mm / PCT_SAMPLE * (double)n_docs;
+
+    // thresholds: hi at the 99.8 % sample quantile; lo = the smallest sample quantile from which on 16 bins
+    // hold fewer than 16 * eps/2 of the values below them
+    // (the top 0.2 % go to the exact list as well: a long right tail would otherwise eat the bins)
+    const uint64_t j_hi = mm - std::max<uint64_t>(64, mm / 512);
+    const uint64_t top = smp[j_hi];
+    const uint64_t hi = top == ~0ull ? top : top + 1;
+    // lo = the smallest sample quantile for which, going by the sample, every window of 16 bins holds fewer than
+    // 16 * eps/2 of the values below it (bins with a single distinct value cost no precision and do not count)
+    uint64_t lo = 0, span = 0;
+    uint32_t shift = 0, mul = 0, n_bins = 0;
+    uint64_t j_lo = 0;
+    bool found = false;
+    for (uint64_t j = std::max<uint64_t>(64, mm / 1024); j <= mm / 8 && !found; j += std::max<uint64_t>(1, j / 4)) {
+        lo = smp[j];
+        if (hi <= lo) break;
+        span = hi - lo;
+        // monotone binning: bin = umulhi(d >> shift, mul) (or d itself when the span is at most PCT_BINS codes)
+        const uint32_t bits = 64 - (uint32_t)__builtin_clzll(span - 1 ? span - 1 : 1);
+        shift = bits > 32 ? bits - 32 : 0;
+        const uint64_t xmax = (span - 1) >> shift;
+        if (xmax + 1 <= PCT_BINS) { mul = 0; n_bins = (uint32_t)(xmax + 1); }
+        else { mul = (uint32_t)(((uint64_t)PCT_BINS << 32) / (xmax + 1)); n_bins = (uint32_t)((xmax * mul) >> 32) + 1; }
+        auto bin_of = [&](uint64_t code) { const uint64_t x = (code - lo) >> shift; return mul ? (uint32_t)((x * mul) >> 32) : (uint32_t)x; };
+        bool ok = true;
+        uint64_t below = j, win_start_below = j, win_count = 0;
+        uint32_t win = 0;
+        for (uint64_t a = j; a <= j_hi && ok;) {
+            const uint32_t bin = bin_of(smp[a]);
+            uint64_t b = a;
+            while (b <= j_hi && bin_of(smp[b]) == bin) b++;
+            if ((bin >> 4) != win) {
+                win = bin >> 4;
+                win_start_below = below;
+                win_count = 0;
+            }
+            if (b - a < 2 || smp[b - 1] != smp[a]) win_count += b - a;
+            if ((double)win_count > 16.0 * (PCT_EPS / 2) * (double)win_start_below) ok = false;
+            below += b - a;
+            a = b;
+        }
+        if (ok) { found = true; j_lo = j; }
+    }
+    if (!found) return 0;
+
+    ExecState::RankState& R = es.rank[k];
+    R = ExecState::RankState();
+    R.lo = lo; R.span = span; R.shift = shift; R.mul = mul; R.n_bins = n_bins;
+    // values outside [lo, hi): the sampled share below lo, plus what lies above the largest sampled value
+    R.tail_cap = (uint64_t)(n_est * ((double)(j_lo + (mm - j_hi)) / (double)mm) * 1.5) + (uint64_t)(n_est / mm * 64) + (1u << 18);
+    const size_t blk = 16 + (size_t)n_bins * 25;
+    if (cudaMallocAsync((void**)&R.d_block, blk, es.st) != cudaSuccess || cudaMallocAsync((void**)&R.d_tail, R.tail_cap * 8 + 16, es.st) != cudaSuccess) {
+        pct_rank_release(es);
+        cudaGetLastError();
+        return 0;  // no room for the list: exact path (which reports its own OOM if it must)
+    }
+    if (cudaMemsetAsync(R.d_block, 0, blk, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "rank table clear failed");
+    R.d_tail_count = (unsigned long long*)R.d_block;
+    R.d_count = (uint64_t*)(R.d_block + 16);
+    R.d_min = R.d_count + n_bins;
+    R.d_max = R.d_min + n_bins;
+    R.d_present = (uint8_t*)(R.d_max + n_bins);
+    R.active = true;
+    return 1;
+}
+
+// Ranks kept from an exactly sorted run of n values: every rank up to 4096, then geometric with ratio 1 + eps/4
+static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks) {
+    ranks.clear();
+    uint64_t dense = std::min<uint64_t>(n, 4096);
+    for (uint64_t r = 1; r <= dense; r++) ranks.push_back(r);
+    uint64_t r = dense;
+    while (r < n) {
+        uint64_t nx = r + std::max<uint64_t>(1, (uint64_t)((double)r * 0.0025));
+        if (nx > n) nx = n;
+        ranks.push_back(nx);
+        r = nx;
+    }
+}
+
+int pct_rank_collect(ExecState& es, int k) {
+    ExecState::RankState& R = es.rank[k];
+    const uint32_t nb = R.n_bins;
+    std::vector<uint8_t> blk(16 + (size_t)nb * 24);
+    CUDA_TRY(cudaMemcpyAsync(blk.data(), R.d_block, blk.size(), cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    unsigned long long tc[2];
+    memcpy(tc, blk.data(), 16);
+    const uint64_t* cnt = (const uint64_t*)(blk.data() + 16);
+    const uint64_t* mn = cnt + nb;  // max-form: ~code
+    const uint64_t* mx = mn + nb;
+    const uint64_t n_tail = tc[0], n_low = tc[1];
+    static const bool trace = getenv("TAGG_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[tagg] rank bins: lo=%016llx span=%016llx shift=%u bins=%u tail=%llu (low %llu) cap=%llu\n", (unsigned long long)R.lo,
+                       (unsigned long long)R.span, R.shift, nb, (unsigned long long)n_tail, (unsigned long long)n_low, (unsigned long long)R.tail_cap);
+    if (n_tail > R.tail_cap || n_low > n_tail) return 0;
+    const uint64_t n_high = n_tail - n_low;
+
+    // precision check on the real counts
+    uint64_t below = n_low, n_binned = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint64_t c = cnt[b];
+        if (!c) continue;
+        if (c > 1 && ~mn[b] != mx[b] && (double)c > std::max(1.0, PCT_EPS * (double)below)) {
+            if (trace) fprintf(stderr, "[tagg] rank bins: bin %u holds %llu values over %llu below it: exact path\n", b, (unsigned long long)c, (unsigned long long)below);
+            return 0;
+        }
+        below += c;
+        n_binned += c;
+    }
+    PctSummary& S = R.summary;
+    S = PctSummary();
+    S.n_total = n_low + n_binned + n_high;
+
+    // the exact lists: sort, keep every low rank up to 4096 then a geometric schedule; the high end evenly thinned
+    std::vector<uint64_t> pos, pos_rank;
+    if (n_tail) {
+        uint64_t* d_sorted = nullptr;
+        void* d_cub = nullptr;
+        size_t cub_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n_tail, 0, 64, es.st);
+        CUDA_TRY(cudaMallocAsync((void**)&d_sorted, n_tail * 8, es.st));
+        es.temps.push_back(d_sorted);
+        CUDA_TRY(cudaMallocAsync(&d_cub, cub_bytes ? cub_bytes : 16, es.st));
+        es.temps.push_back(d_cub);
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_cub, cub_bytes, (const uint64_t*)R.d_tail, d_sorted, (int)n_tail, 0, 64, es.st));
+        std::vector<uint64_t> rk;
+        rank_schedule(n_low, rk);
+        for (uint64_t r : rk) { pos.push_back(r - 1); pos_rank.push_back(r); }
+        const uint64_t step = std::max<uint64_t>(1, n_high / 4096);
+        for (uint64_t i = 0; i < n_high; i += step) { pos.push_back(n_low + i); pos_rank.push_back(n_low + n_binned + i + 1); }
+        if (n_high && pos.back() != n_tail - 1) { pos.push_back(n_tail - 1); pos_rank.push_back(S.n_total); }
+        uint64_t *d_pos = nullptr, *d_out = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&d_pos, pos.size() * 8 + 16, es.st));
+        es.temps.push_back(d_pos);
+        CUDA_TRY(cudaMallocAsync((void**)&d_out, pos.size() * 8 + 16, es.st));
+        es.temps.push_back(d_out);
+        std::vector<uint64_t> vals(pos.size());
+        if (!pos.empty()) {
+            CUDA_TRY(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, es.st));
+            k_gather_u64<<<(unsigned)std::min<uint64_t>((pos.size() + 255) / 256, 1024), 256, 0, es.st>>>(d_sorted, d_pos, pos.size(), d_out);
+            es.ctx->launches++;
+            es.n_launches++;
+            CUDA_TRY(cudaMemcpyAsync(vals.data(), d_out, pos.size() * 8, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaStreamSynchronize(es.st));
+        }
+        size_t i = 0;
+        for (; i < pos.size() && pos[i] < n_low; i++) { S.ranks.push_back(pos_rank[i]); S.value_bits.push_back(code_to_f64_bits(vals[i])); }
+        below = n_low;
+        for (uint32_t b = 0; b < nb; b++) {
+            if (!cnt[b]) continue;
+            S.ranks.push_back(below + 1); S.value_bits.push_back(code_to_f64_bits(~mn[b]));
+            if (cnt[b] > 1) { S.ranks.push_back(below + cnt[b]); S.value_bits.push_back(code_to_f64_bits(mx[b])); }
+            below += cnt[b];
+        }
+        for (; i < pos.size(); i++) { S.ranks.push_back(pos_rank[i]); S.value_bits.push_back(code_to_f64_bits(vals[i])); }
+    } else {
+        below = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            if (!cnt[b]) continue;
+            S.ranks.push_back(below + 1); S.value_bits.push_back(code_to_f64_bits(~mn[b]));
+            if (cnt[b] > 1) { S.ranks.push_back(below + cnt[b]); S.value_bits.push_back(code_to_f64_bits(mx[b])); }
+            below += cnt[b];
+        }
+    }
+    return 1;
+}

@@ -81,6 +81,14 @@ static int read_percentiles(ExecState& es, tagg_result* res) {
     const PlanMeta& m = *es.meta;
     res->pcts.resize(m.pct_node.size());
     for (size_t k = 0; k < m.pct_node.size(); k++) {
+        if (es.rank[k].active) {  // rank-bin mode: collected (and checked) in exec_run
+            res->pcts[k][0] = std::move(es.rank[k].summary);
+            continue;
+        }
+        if (!es.pct_count[k]) {  // never materialised (no candidate reached the leaf's launch)
+            res->pcts[k][0] = PctSummary();
+            continue;
+        }
         PctSummary sum;
         unsigned long long n = 0;
         CUDA_TRY(cudaMemcpyAsync(&n, es.pct_count[k], 8, cudaMemcpyDeviceToHost, es.st));

@@ -42,6 +42,7 @@
 #define ST_MAXBITS (2 + ST_MAXPRED)
 #define ST_MAXRG 4
 #define ST_MAXBG 3
+#define ST_TBUF 128                                  // BK_RANK: out-of-range codes buffered per warp
 
 enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2 };
 enum { OPB_SUM = 1, OPB_MIN = 2, OPB_MAX = 4 };
@@ -87,10 +88,10 @@ struct SParams {
     int32_t key_scol;
     uint64_t dom_min, dom_size;
     double f0, f1;
-    // BK_RANK (percentiles): rank bins delimited by sorted code boundaries (bounds[0] = tail threshold); codes below
-    // the threshold are appended to an exact tail list instead
-    const uint64_t* rank_bounds;
-    uint32_t soff_rank_bounds;
+    // BK_RANK (percentiles, pct.cu): monotone code bins umulhi((code - rank_lo) >> rank_shift, rank_mul) over [rank_lo, rank_lo + rank_span);
+    // codes outside are appended to an exact list (tail_count[0] = appended, [1] = those below rank_lo)
+    uint64_t rank_lo, rank_span;
+    uint32_t rank_shift, rank_mul;
     uint64_t* tail_codes;
     unsigned long long* tail_count;
     uint64_t tail_cap;
@@ -250,11 +251,6 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
     if (STAB) {
         uint32_t* t32 = (uint32_t*)smem;
         for (uint32_t i = tid; i < p.table_bytes / 4; i += blockDim.x) t32[i] = 0;
-        if (BUCKET == BK_RANK) {
-            __syncthreads();
-            uint64_t* b = (uint64_t*)(smem + p.soff_rank_bounds);
-            for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x) b[i] = p.rank_bounds[i];
-        }
     }
     __syncthreads();
 
@@ -323,6 +319,9 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
         uint32_t matched = 0;  // every lane holds the warp's count
 
+        // BK_RANK: this warp's buffer of out-of-range codes (the last ST_WARPS * ST_TBUF * 8 bytes of the group block)
+        const uint32_t tbuf_saddr = smem_u32(gbase + p.group_bytes - (ST_WARPS - warp) * ST_TBUF * 8);
+        uint32_t wtail = 0;
         const uint32_t full_saddr = smem_u32(full), empty_saddr = smem_u32(empty);
         uint32_t stage = 0, parity = 0;
         for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
@@ -386,6 +385,25 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
             for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
 
+            auto flush_tail = [&]() {  // warp-uniform: wtail buffered codes -> the global list
+                __syncwarp();
+                unsigned long long base = 0;
+                uint32_t nlow = 0;
+                for (uint32_t i = lane; i < wtail; i += 32) nlow += lds64(tbuf_saddr + 8 * i) < p.rank_lo ? 1u : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+                if (lane == 0) {
+                    base = atomicAdd(p.tail_count, (unsigned long long)wtail);
+                    if (nlow) atomicAdd(p.tail_count + 1, (unsigned long long)nlow);
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (uint32_t i = lane; i < wtail; i += 32) {
+                    if (base + i < p.tail_cap) p.tail_codes[base + i] = lds64(tbuf_saddr + 8 * i);
+                    else *p.overflow_flag = 3u;
+                }
+                __syncwarp();
+                wtail = 0;
+            };
             // U matched documents per lane at a time (independent chains overlap the table latency).
             // CHECK: slots may be empty (act[u] false) — the ragged tail; otherwise every slot is live.
             auto process = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
@@ -429,17 +447,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 rel[u] = lo + krel;
                                 act[u] = rel[u] < dom_size32;
                             } else if (BUCKET == BK_RANK) {
-                                // rank bin = last boundary <= code (branch-free binary search in shared memory)
                                 const uint64_t code = tget(kc, dl[u]);
-                                const uint32_t bsa = smem_saddr + p.soff_rank_bounds;
-                                uint32_t lo = 0, len = dom_size32;
-                                while (len > 1) {
-                                    const uint32_t half = len >> 1;
-                                    if (lds64(bsa + 8 * (lo + half)) <= code) lo += half;
-                                    len -= half;
-                                }
-                                rel[u] = lo;
-                                tail[u] = code < lds64(bsa);
+                                const uint64_t d = code - p.rank_lo;  // below rank_lo: wraps above the span
+                                rel[u] = (uint32_t)(d >> p.rank_shift);
+                                if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
+                                tail[u] = d >= p.rank_span;
                                 tail_code[u] = code;
                             } else {
                                 uint64_t ord;
@@ -450,20 +462,19 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         }
                     }
                     if (BUCKET == BK_RANK) {
-                        // values below the first boundary go to the exact tail list: one atomic per warp and slot
+                        // values outside the binned range go to the exact list, through a per-warp buffer in shared
+                        // memory: one global atomic per ST_TBUF values (a single hot counter serialises in L2)
 #pragma unroll
                         for (int u = 0; u < U; u++) {
                             const uint32_t tm = __ballot_sync(0xffffffffu, tail[u]);
                             if (tm) {
-                                unsigned long long base = 0;
-                                if (lane == (uint32_t)(__ffs(tm) - 1)) base = atomicAdd(p.tail_count, (unsigned long long)__popc(tm));
-                                base = __shfl_sync(0xffffffffu, base, __ffs(tm) - 1);
+                                if (wtail + __popc(tm) > ST_TBUF) flush_tail();
                                 if (tail[u]) {
-                                    const unsigned long long at = base + __popc(tm & lt_mask);
-                                    if (at < p.tail_cap) p.tail_codes[at] = tail_code[u];
-                                    else *p.overflow_flag = 3u;
+                                    const uint32_t at = wtail + __popc(tm & lt_mask);
+                                    asm volatile("st.shared.u64 [%0], %1;" ::"r"(tbuf_saddr + 8 * at), "l"(tail_code[u]) : "memory");
                                     act[u] = false;
                                 }
+                                wtail += __popc(tm);
                             }
                         }
                     }
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         for (int u = 0; u < U; u++) {
                             code[u] = 0; cur_min[u] = ~0ull; cur_max[u] = ~0ull;
                             if (act[u]) {
-                                code[u] = tget(bc[g], dl[u]);
+                                code[u] = BUCKET == BK_RANK ? tail_code[u] : tget(bc[g], dl[u]);
                                 if (ops & OPB_MIN) cur_min[u] = STAB ? lds64(smem_saddr + p.soff_tab_min[g] + 8 * rel[u]) : G.acc_min[rel[u]];
                                 if (ops & OPB_MAX) cur_max[u] = STAB ? lds64(smem_saddr + p.soff_tab_max[g] + 8 * rel[u]) : G.acc_max[rel[u]];
                             }
@@ -587,6 +598,24 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             if (++stage == S) { stage = 0; parity ^= 1u; }
         }
 
+        if (BUCKET == BK_RANK && wtail) {
+            // (the lambda lives inside the tile loop; same steps here for the last partial buffer)
+            __syncwarp();
+            unsigned long long base = 0;
+            uint32_t nlow = 0;
+            for (uint32_t i = lane; i < wtail; i += 32) nlow += lds64(tbuf_saddr + 8 * i) < p.rank_lo ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+            if (lane == 0) {
+                base = atomicAdd(p.tail_count, (unsigned long long)wtail);
+                if (nlow) atomicAdd(p.tail_count + 1, (unsigned long long)nlow);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < wtail; i += 32) {
+                if (base + i < p.tail_cap) p.tail_codes[base + i] = lds64(tbuf_saddr + 8 * i);
+                else *p.overflow_flag = 3u;
+            }
+        }
         // fold the root accumulators (warp shuffle, then one atomic per warp)
         if (lane == 0 && matched) {
             if (p.n_root_counts > 0) atomicAdd((unsigned long long*)p.root_count_acc[0], (unsigned long long)matched);
@@ -870,6 +899,35 @@ static int stream_launch(ExecState& es, bool first_launch) {
             int save_n = n_rgroups;
             if (add_fold(es, sh, sp.rgroups, n_rgroups, ST_MAXRG, (int)mem)) covered.push_back(mem);
             else { sh = save; n_rgroups = save_n; }
+        } else if (nd.op == TAGG_OP_PERCENTILES) {
+            // K4 on the streaming path: rank bins between sampled thresholds (pct.cu)
+            if (bucket_mode != BK_NONE || nd.multi || n_bgroups > 0) continue;
+            const int k = m.pct_of[mem];
+            Shape save = sh;
+            const int scol = sh.stage_col(m.col_slot[mem]);
+            if (scol < 0) { sh = save; continue; }
+            const int rc = pct_rank_plan(es, mem, k);
+            if (rc < 0) return rc;
+            if (rc == 0) { sh = save; continue; }
+            const ExecState::RankState& R = es.rank[k];
+            bucket_mode = BK_RANK;
+            sp.key_scol = scol;
+            sp.dom_min = 0;
+            sp.dom_size = R.n_bins;
+            sp.rank_lo = R.lo; sp.rank_span = R.span; sp.rank_shift = R.shift; sp.rank_mul = R.mul;
+            sp.tail_codes = R.d_tail; sp.tail_count = R.d_tail_count; sp.tail_cap = R.tail_cap;
+            sp.overflow_flag = (uint32_t*)(es.arena + es.off_overflow);
+            sp.present = R.d_present;
+            sp.n_bcounts = 1;
+            sp.bcount_acc[0] = R.d_count;
+            SGroup& G = sp.bgroups[n_bgroups++];
+            memset(&G, 0, sizeof(G));
+            G.scol = scol;
+            G.kind = TAGG_F64;
+            G.ops = OPB_MIN | OPB_MAX;
+            G.acc_min = R.d_min;
+            G.acc_max = R.d_max;
+            covered.push_back(mem);
         } else if (nd.op == TAGG_OP_TERMS || nd.op == TAGG_OP_HISTOGRAM) {
             if (bucket_mode != BK_NONE || nd.multi) continue;  // one bucket node per launch; multi-valued: generic kernel
             const int sc = m.own_scope[mem];
@@ -990,7 +1048,9 @@ static int stream_launch(ExecState& es, bool first_launch) {
     const size_t SMEM_MAX = 225 * 1024;
     auto group_bytes = [&](uint32_t stages) {
         size_t b = (size_t)stages * sp.stage_bytes + ST_WARPS * ST_DOCS_PER_WARP * 2 + (size_t)stages * sizeof(TileDesc) + 2 * stages * 8;
-        return (b + 127) & ~(size_t)127;
+        b = (b + 127) & ~(size_t)127;
+        if (bucket_mode == BK_RANK) b += ST_WARPS * ST_TBUF * 8;  // per-warp buffers of out-of-range codes
+        return b;
     };
     size_t table_bytes = 0;
     bool stab = false;
@@ -1013,6 +1073,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
             if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
         if (!ok) { stab = false; table_bytes = 0; }
     }
+    if (bucket_mode == BK_RANK && !stab) return -tagg_fail(TAGG_ERR_CUDA, "rank-bin tables do not fit shared memory (internal sizing error)");
     if (!stab) {
         n_groups = 1;
         n_stages = group_bytes(3) <= SMEM_MAX ? 3 : 2;
