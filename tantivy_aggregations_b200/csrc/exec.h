@@ -1,6 +1,37 @@
 // exec.h — state of one tagg_execute call, shared by exec.cu / stream.cu / result.cu / comm.cu.
 #pragma once
+#include <string.h>
+
+#include <cmath>
+
 #include "host.h"
+
+// host twins of the device codecs (dev.cuh)
+inline double code_to_f64_h(uint64_t c) {
+    uint64_t bits = (c >> 63) ? (c ^ 0x8000000000000000ull) : ~c;
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+}
+// host twin of dev.cuh hist_ord (IEEE double arithmetic is identical on both sides)
+inline bool hist_ord_h(uint64_t code, double start, double interval, uint64_t* ord) {
+    double k = code_to_f64_h(code);
+    if (k != k) return false;
+    volatile double n = k - start;
+    if (n < 0.0) return false;
+    volatile double q0 = n / interval;
+    double q = std::floor(q0);
+    if (!(q == q) || q <= 0.0) *ord = 0;
+    else if (q >= 18446744073709551616.0) *ord = ~0ull;
+    else *ord = (uint64_t)q;
+    return true;
+}
+inline uint64_t f64_to_code_h(double v) {
+    uint64_t bits;
+    memcpy(&bits, &v, 8);
+    return (bits >> 63) == 0 ? bits ^ 0x8000000000000000ull : ~bits;
+}
+
 
 struct ScopeLayout {
     int mode = SCOPE_DENSE;

@@ -96,6 +96,12 @@ struct SParams {
     unsigned long long* tail_count;
     uint64_t tail_cap;
     uint32_t* overflow_flag;
+    // BK_HIST with few buckets: hist_bounds[j] = smallest code whose ordinal is >= dom_min + j (j = 0..dom_size; entry
+    // dom_size closes the valid range) — the exact IEEE division of histogram.rs:146 becomes a multiply + table fix-up
+    const uint64_t* hist_bounds;
+    uint32_t soff_hist_bounds;
+    double hist_inv;
+    uint32_t soff_present_bits;  // global tables without a count: CTA bitmap of touched buckets (0 = none), flushed at the end
     uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
     uint8_t* present_out;  // STAB: written by the final table merge
     int32_t n_bcounts;
@@ -248,9 +254,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         for (uint32_t s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, ST_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (STAB) {
+    {   // shared tables (STAB) / presence bitmap / histogram boundaries live in front of the group blocks
         uint32_t* t32 = (uint32_t*)smem;
         for (uint32_t i = tid; i < p.table_bytes / 4; i += blockDim.x) t32[i] = 0;
+        if (BUCKET == BK_HIST && p.hist_bounds) {
+            __syncthreads();
+            uint64_t* b = (uint64_t*)(smem + p.soff_hist_bounds);
+            for (uint32_t i = tid; i <= (uint32_t)p.dom_size; i += blockDim.x) b[i] = p.hist_bounds[i];
+        }
     }
     __syncthreads();
 
@@ -317,6 +328,19 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         bool rseen = false;
 #pragma unroll
         for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
+        // CT root shape (one f64 column, compile-time ops): min / max run on the packed deltas and are folded into
+        // the code domain only when the column's min_value changes (segment change); the sum adds delta + constant
+        constexpr bool CTROOT = SH::ROPS >= 0 && NRG == 1;
+        uint64_t dmin = ~0ull, dmax = 0, cminv = 0;
+        bool fseen = false;
+        auto fold_root = [&]() {
+            if (fseen) {
+                const uint64_t cmax = dmax + cminv, cmin = ~(dmin + cminv);
+                rmax[0] = cmax > rmax[0] ? cmax : rmax[0];
+                rmin[0] = cmin > rmin[0] ? cmin : rmin[0];
+            }
+            dmin = ~0ull; dmax = 0; fseen = false;
+        };
         uint32_t matched = 0;  // every lane holds the warp's count
 
         // BK_RANK: this warp's buffer of out-of-range codes (the last ST_WARPS * ST_TBUF * 8 bytes of the group block)
@@ -385,6 +409,25 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
             for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
 
+            // every f64 column this tile touches is non-negative (min_value's sign bit): code -> f64 is one XOR
+            bool fpos = true;
+            if (BUCKET == BK_HIST || BUCKET == BK_RANK) fpos = fpos && (kc.minhi >> 31);
+#pragma unroll
+            for (int g = 0; g < NBG; g++) fpos = fpos && (p.bgroups[g].kind != TAGG_F64 || (bc[g].minhi >> 31));
+#pragma unroll
+            for (int g = 0; g < NRG; g++) fpos = fpos && (p.rgroups[g].kind != TAGG_F64 || (rc[g].minhi >> 31));
+            uint64_t rbase = 0;  // CT root: f64 bits = delta + rbase when fpos
+            if (CTROOT) {
+                const uint64_t mv = ((uint64_t)rc[0].minhi << 32) | rc[0].minlo;
+                if (mv != cminv) { fold_root(); cminv = mv; }
+                rbase = mv ^ 0x8000000000000000ull;
+            }
+            // histogram: ordinal via multiply + boundary fix-up (exact), see SParams::hist_bounds
+            const bool hb = BUCKET == BK_HIST && p.hist_bounds != nullptr;
+            const uint32_t hb_saddr = smem_saddr + p.soff_hist_bounds;
+            uint64_t hb_first = 0, hb_end = 0;
+            if (hb) { hb_first = lds64(hb_saddr); hb_end = lds64(hb_saddr + 8 * dom_size32); }
+
             auto flush_tail = [&]() {  // warp-uniform: wtail buffered codes -> the global list
                 __syncwarp();
                 unsigned long long base = 0;
@@ -406,14 +449,33 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             };
             // U matched documents per lane at a time (independent chains overlap the table latency).
             // CHECK: slots may be empty (act[u] false) — the ragged tail; otherwise every slot is live.
-            auto process = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
+            auto process = [&](auto U_, auto CHECK_, auto POS_, const uint32_t* dl, const bool* act_in) {
                 constexpr int U = decltype(U_)::value;
                 constexpr bool CHECK = decltype(CHECK_)::value;
+                constexpr bool POS = decltype(POS_)::value;
+                auto c2f = [](uint64_t code) { return POS ? __longlong_as_double((long long)(code ^ 0x8000000000000000ull)) : code_to_f64(code); };
                 bool act[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) { act[u] = CHECK ? act_in[u] : true; rseen = rseen || act[u]; }
+                if (CTROOT) {
 #pragma unroll
-                for (int g = 0; g < NRG; g++) {
+                    for (int u = 0; u < U; u++) {
+                        if (act[u]) {
+                            uint32_t lo, hi;
+                            tdelta(rc[0], dl[u], lo, hi);
+                            const uint64_t d = ((uint64_t)hi << 32) | lo;
+                            if (SH::ROPS & OPB_SUM) {
+                                const double v = POS ? __longlong_as_double((long long)(d + rbase)) : code_to_f64(d + cminv);
+                                rsum[0] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[0]), v));
+                            }
+                            if (SH::ROPS & OPB_MIN) dmin = d < dmin ? d : dmin;
+                            if (SH::ROPS & OPB_MAX) dmax = d > dmax ? d : dmax;
+                            fseen = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < (CTROOT ? 0 : NRG); g++) {
                     const SGroup& G = p.rgroups[g];
                     const uint32_t ops = g == 0 ? ops_r0 : G.ops;
                     if (ops) {
@@ -422,7 +484,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             if (act[u]) {
                                 uint64_t code = tget(rc[g], dl[u]);
                                 if (ops & OPB_SUM) {
-                                    if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), code_to_f64(code)));
+                                    if (G.kind == TAGG_F64) rsum[g] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[g]), c2f(code)));
                                     else rsum[g] += code_to_bits(G.kind, code);
                                 }
                                 if (ops & OPB_MIN) { uint64_t v = ~code; rmin[g] = v > rmin[g] ? v : rmin[g]; }
@@ -453,6 +515,20 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
                                 tail[u] = d >= p.rank_span;
                                 tail_code[u] = code;
+                            } else if (hb) {
+                                // NaN or below start lie outside [hb_first, hb_end): skipped (histogram.rs:138-145)
+                                const uint64_t code = tget(kc, dl[u]);
+                                if (code < hb_first || code >= hb_end) {
+                                    act[u] = false;
+                                } else {
+                                    const double t = __dmul_rn(__dsub_rn(c2f(code), p.f0), p.hist_inv);
+                                    long long j = (long long)t - (long long)p.dom_min;  // near the exact ordinal; the table decides
+                                    j = j < 0 ? 0 : (j >= (long long)dom_size32 ? (long long)dom_size32 - 1 : j);
+                                    uint32_t r = (uint32_t)j;
+                                    while (code < lds64(hb_saddr + 8 * r)) r--;
+                                    while (code >= lds64(hb_saddr + 8 * (r + 1))) r++;
+                                    rel[u] = r;
+                                }
                             } else {
                                 uint64_t ord;
                                 // NaN or below start: skipped (histogram.rs:138-145)
@@ -488,7 +564,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             } else {
                                 if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel[u]), 1ull);
                                 if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel[u]), 1ull);
-                                if (p.present && !p.present[rel[u]]) p.present[rel[u]] = 1;  // only when no count names the bucket
+                                if (p.soff_present_bits) {  // no count names the bucket: CTA bitmap, flushed once at the end
+                                    const uint32_t wa = smem_saddr + p.soff_present_bits + 4 * (rel[u] >> 5), bit = 1u << (rel[u] & 31);
+                                    if (!(lds32(wa) & bit)) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(bit) : "memory");
+                                } else if (p.present && !p.present[rel[u]]) {
+                                    p.present[rel[u]] = 1;
+                                }
                             }
                         }
                     }
@@ -514,7 +595,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             if (act[u]) {
                                 if (ops & OPB_SUM) {
                                     uint64_t* a = STAB ? (uint64_t*)(smem + p.soff_tab_sum[g]) + rel[u] : G.acc_sum + rel[u];
-                                    if (G.kind == TAGG_F64) atomicAdd((double*)a, code_to_f64(code[u]));
+                                    if (G.kind == TAGG_F64) atomicAdd((double*)a, c2f(code[u]));
                                     else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code[u]));
                                 }
                                 if ((ops & OPB_MIN) && cur_min[u] < ~code[u]) {
@@ -529,6 +610,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         }
                     }
                 }
+            };
+            // the non-negative fast path is instantiated where it pays: CT shapes and histograms
+            constexpr bool HAS_POS = SH::BOPS >= 0 || SH::ROPS >= 0 || BUCKET == BK_HIST || BUCKET == BK_RANK;
+            auto run = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
+                if (HAS_POS && fpos) process(U_, CHECK_, std::true_type{}, dl, act_in);
+                else process(U_, CHECK_, std::false_type{}, dl, act_in);
             };
             using I1 = std::integral_constant<int, 1>;
             using I2 = std::integral_constant<int, 2>;
@@ -556,7 +643,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
                     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d1) : "r"(q_saddr + 2 * (j0 + 32 + lane)));
                     dl[0] = d0; dl[1] = d1;
-                    process(I2{}, std::false_type{}, dl, nullptr);
+                    run(I2{}, std::false_type{}, dl, nullptr);
                 }
                 for (; j0 < nq; j0 += 32) {
                     uint32_t dl[1];
@@ -565,7 +652,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     uint16_t d0 = 0;
                     if (act[0]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
                     dl[0] = d0;
-                    process(I1{}, std::true_type{}, dl, act);
+                    run(I1{}, std::true_type{}, dl, act);
                 }
             } else {
                 // nothing narrows the doc stream: every document of the tile is matched (ragged only in a
@@ -578,7 +665,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         uint32_t dl[4];
 #pragma unroll
                         for (int u = 0; u < 4; u++) dl[u] = wbase + (j0 + u) * 32 + lane;
-                        process(I4{}, std::false_type{}, dl, nullptr);
+                        run(I4{}, std::false_type{}, dl, nullptr);
                     }
                 } else {
 #pragma unroll 1
@@ -589,7 +676,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         bool act[1];
                         dl[0] = wbase + j * 32 + lane;
                         act[0] = (mj >> lane) & 1u;
-                        process(I1{}, std::true_type{}, dl, act);
+                        run(I1{}, std::true_type{}, dl, act);
                     }
                 }
             }
@@ -598,6 +685,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             if (++stage == S) { stage = 0; parity ^= 1u; }
         }
 
+        if (CTROOT) fold_root();
         if (BUCKET == BK_RANK && wtail) {
             // (the lambda lives inside the tile loop; same steps here for the last partial buffer)
             __syncwarp();
@@ -649,6 +737,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         }
     }
 
+    if (!STAB && BUCKET == BK_TERMS && p.soff_present_bits) {
+        __syncthreads();
+        const uint32_t* bm = (const uint32_t*)(smem + p.soff_present_bits);
+        for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x)
+            if ((bm[i >> 5] >> (i & 31)) & 1u) p.present_out[i] = 1;
+    }
     if (STAB) {
         // merge the CTA's private tables into the global ones; count table 0 always exists in STAB mode
         // (hidden when the plan has no count) and is the record of which buckets exist
@@ -723,7 +817,6 @@ template <int BUCKET, int NBG>
 static stream_fn pick_nrg(int nrg, bool compact, bool stab) {
     switch (nrg) {
         case 0: return pick_flags<BUCKET, NBG, 0>(compact, stab);
-        case 1: return pick_flags<BUCKET, NBG, 1>(compact, stab);
         default: return pick_flags<BUCKET, NBG, ST_MAXRG>(compact, stab);
     }
 }
@@ -731,7 +824,6 @@ template <int BUCKET>
 static stream_fn pick_nbg(int nbg, int nrg, bool compact, bool stab) {
     switch (nbg) {
         case 0: return pick_nrg<BUCKET, 0>(nrg, compact, stab);
-        case 1: return pick_nrg<BUCKET, 1>(nrg, compact, stab);
         default: return pick_nrg<BUCKET, 3>(nrg, compact, stab);
     }
 }
@@ -745,7 +837,7 @@ template <int ROPS>
 static stream_fn pick_ct_root(bool compact) {
     return compact ? (stream_fn)k_stream<Shp<BK_NONE, 0, 1, true, false, -1, ROPS>> : (stream_fn)k_stream<Shp<BK_NONE, 0, 1, false, false, -1, ROPS>>;
 }
-static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0) {
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0, bool r0_f64) {
     if (bucket == BK_TERMS && nbg == 1 && nrg == 0) {
         switch (bops0) {
             case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab);
@@ -755,7 +847,7 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
         }
     }
     if (bucket == BK_RANK) return pick_ct_bucket<BK_RANK, (OPB_MIN | OPB_MAX)>(compact, true);
-    if (bucket == BK_NONE && nrg == 1) {
+    if (bucket == BK_NONE && nrg == 1 && r0_f64) {
         switch (rops0) {
             case OPB_MIN: return pick_ct_root<OPB_MIN>(compact);
             case OPB_MAX: return pick_ct_root<OPB_MAX>(compact);
@@ -763,12 +855,17 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
             case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_root<(OPB_MIN | OPB_MAX | OPB_SUM)>(compact);
         }
     }
-    if (nbg == 2) nbg = 3;
     switch (bucket) {
         case BK_NONE: return pick_nrg<BK_NONE, 0>(nrg, compact, false);
         case BK_TERMS: return pick_nbg<BK_TERMS>(nbg, nrg, compact, stab);
         default: return pick_nbg<BK_HIST>(nbg, nrg, compact, stab);
     }
+}
+
+static bool j_monotone(const std::vector<uint64_t>& b) {
+    for (size_t i = 1; i < b.size(); i++)
+        if (b[i] < b[i - 1]) return false;
+    return true;
 }
 
 struct Shape {
@@ -1065,19 +1162,82 @@ static int stream_launch(ExecState& es, bool first_launch) {
         }
         if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
     }
+    // histogram with few buckets: exact code boundaries of the ordinals (host: a guess from start + o * interval,
+    // then a local search on the exact IEEE expression, which is monotone in the code)
+    if (bucket_mode == BK_HIST && stab && sp.dom_size <= 256 && tiles_total >= 2048) {
+        const double start = sp.f0, interval = sp.f1;
+        const uint64_t top = f64_to_code_h(INFINITY);
+        auto reaches = [&](uint64_t c, uint64_t o) { uint64_t ord; return c <= top && hist_ord_h(c, start, interval, &ord) && ord >= o; };
+        std::vector<uint64_t> B(sp.dom_size + 1);
+        bool ok = true;
+        for (uint64_t j = 0; j <= sp.dom_size && ok; j++) {
+            const uint64_t o = sp.dom_min + j;
+            // smallest code c <= top with reaches(c, o); top + 1 if none
+            if (!reaches(top, o)) { B[j] = top + 1; continue; }
+            uint64_t g = f64_to_code_h(start + (double)o * interval);
+            if (g > top) g = top;
+            uint64_t lo, hi;  // invariant: !reaches(lo) (or lo == 0 unknown), reaches(hi)
+            if (reaches(g, o)) {
+                hi = g;
+                uint64_t step = 1;
+                lo = g;
+                while (true) {
+                    if (lo < step) { lo = 0; break; }
+                    lo -= step;
+                    if (!reaches(lo, o)) break;
+                    hi = lo;
+                    step <<= 1;
+                }
+                if (lo == 0 && reaches(0, o)) { B[j] = 0; continue; }
+            } else {
+                lo = g;
+                uint64_t step = 1;
+                hi = g;
+                while (true) {
+                    hi = top - hi < step ? top : hi + step;
+                    if (reaches(hi, o)) break;
+                    lo = hi;
+                    step <<= 1;
+                }
+            }
+            while (hi - lo > 1) {
+                const uint64_t mid = lo + (hi - lo) / 2;
+                if (reaches(mid, o)) hi = mid; else lo = mid;
+            }
+            B[j] = hi;
+        }
+        if (j_monotone(B)) {
+            uint64_t* d_b = nullptr;
+            if (cudaMallocAsync((void**)&d_b, B.size() * 8, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "histogram boundary table allocation failed");
+            es.temps.push_back(d_b);
+            if (cudaMemcpyAsync(d_b, es.pin(B.data(), B.size() * 8), B.size() * 8, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
+                return -tagg_fail(TAGG_ERR_CUDA, "histogram boundary table upload failed");
+            sp.hist_bounds = d_b;
+            sp.hist_inv = 1.0 / interval;
+            sp.soff_hist_bounds = (uint32_t)table_bytes;
+            table_bytes += (B.size() * 8 + 127) & ~(size_t)127;
+        }
+    }
+    // global tables that no count names: bucket existence through a CTA bitmap in shared memory
+    if (bucket_mode == BK_TERMS && !stab && sp.n_bcounts == 0 && sp.dom_size <= (1u << 20)) {
+        sp.soff_present_bits = 128;
+        table_bytes = 128 + ((((size_t)sp.dom_size + 31) / 32 * 4 + 127) & ~(size_t)127);
+    }
     uint32_t n_groups = 1, n_stages = 3;
     if (stab) {
         const uint32_t cand[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
         bool ok = false;
         for (auto& c : cand)
             if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
-        if (!ok) { stab = false; table_bytes = 0; }
+        if (!ok) { stab = false; table_bytes = 0; sp.hist_bounds = nullptr; }
     }
     if (bucket_mode == BK_RANK && !stab) return -tagg_fail(TAGG_ERR_CUDA, "rank-bin tables do not fit shared memory (internal sizing error)");
     if (!stab) {
+        // one group per CTA, several CTAs per SM: take the ring depth that keeps the most consumer warps resident
         n_groups = 1;
-        n_stages = group_bytes(3) <= SMEM_MAX ? 3 : 2;
-        if (group_bytes(n_stages) > SMEM_MAX) return 0;
+        if (table_bytes + group_bytes(2) > SMEM_MAX) return 0;
+        const size_t per3 = SMEM_MAX / (table_bytes + group_bytes(3) + 1024), per2 = SMEM_MAX / (table_bytes + group_bytes(2) + 1024);
+        n_stages = (per3 >= 1 && per3 >= std::min<size_t>(per2, 4)) ? 3 : 2;
     }
     sp.n_stages = n_stages;
     sp.group_bytes = (uint32_t)group_bytes(n_stages);
@@ -1088,8 +1248,8 @@ static int stream_launch(ExecState& es, bool first_launch) {
     if (bucket_mode != BK_NONE && (sp.n_bcounts > 0 || stab)) sp.present = nullptr;  // derived from the counts
 
     // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
-    int nrg_t = n_rgroups <= 1 ? n_rgroups : ST_MAXRG;
-    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u);
+    int nrg_t = n_rgroups;
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u, n_rgroups && sp.rgroups[0].kind == TAGG_F64);
     static std::mutex attr_mu;
     static std::vector<stream_fn> attr_done;
     {
