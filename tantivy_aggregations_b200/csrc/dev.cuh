@@ -21,6 +21,7 @@
 struct DevColumn {
     const uint64_t* words;  // packed payload viewed as little-endian u64 words
     uint64_t min_value;
+    uint64_t max_value;     // min_value + amplitude
     uint64_t mask;
     uint64_t n_values;
     uint32_t num_bits;

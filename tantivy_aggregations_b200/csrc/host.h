@@ -67,6 +67,7 @@ struct HostColumn {
         DevColumn d;
         d.words = (const uint64_t*)dptr;
         d.min_value = min_value;
+        d.max_value = min_value + amplitude;
         d.mask = num_bits == 64 ? ~0ull : ((1ull << num_bits) - 1ull);
         d.n_values = n_values;
         d.num_bits = num_bits;

@@ -23,6 +23,8 @@
 // check-before-atomic (cells only move monotonically, so a stale read can only cause a redundant
 // atomic, never a wrong skip).  The kernel is a template over the number of root / bucket column
 // groups so every per-tile column descriptor lives in registers.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -47,7 +49,8 @@
 enum { PR_FILTER = 0, PR_RANGE = 1, PR_LUT = 2 };
 enum { OPB_SUM = 1, OPB_MIN = 2, OPB_MAX = 4 };
 enum { BK_NONE = 0, BK_TERMS = 1, BK_HIST = 2, BK_RANK = 3 };
-enum { SF_MAIN_BITS = 1, SF_DELETES = 2, SF_PRED_BITS0 = 4 /* << i */, SF_PRED_NONE0 = 256 /* << i */ };
+enum { SF_MAIN_BITS = 1, SF_DELETES = 2, SF_PRED_BITS0 = 4 /* << i */, SF_PRED_NONE0 = 256 /* << i */,
+       SF_FPOS = 4096 /* every staged f64 column of the segment lies in [+0.0, +inf]: no sign handling, no NaN */ };
 
 // Everything the kernel needs to know about one segment, prepared on the host.
 struct SegDesc {
@@ -101,6 +104,12 @@ struct SParams {
     const uint64_t* hist_bounds;
     uint32_t soff_hist_bounds;
     double hist_inv;
+    // BK_RANK + histogram_agg_f64(same column, count_agg()) of the same tuple, fused into the percentile pass:
+    // bucket counts in a second shared table (boundary-table ordinals, side_dom buckets from ordinal side_dom_min)
+    uint32_t side_dom, soff_side_count;
+    uint64_t side_dom_min;
+    uint64_t* side_count_acc;
+    uint8_t* side_present;
     uint32_t soff_present_bits;  // global tables without a count: CTA bitmap of touched buckets (0 = none), flushed at the end
     uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
     uint8_t* present_out;  // STAB: written by the final table merge
@@ -257,10 +266,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
     {   // shared tables (STAB) / presence bitmap / histogram boundaries live in front of the group blocks
         uint32_t* t32 = (uint32_t*)smem;
         for (uint32_t i = tid; i < p.table_bytes / 4; i += blockDim.x) t32[i] = 0;
-        if (BUCKET == BK_HIST && p.hist_bounds) {
+        if ((BUCKET == BK_HIST || BUCKET == BK_RANK) && p.hist_bounds) {
             __syncthreads();
             uint64_t* b = (uint64_t*)(smem + p.soff_hist_bounds);
-            for (uint32_t i = tid; i <= (uint32_t)p.dom_size; i += blockDim.x) b[i] = p.hist_bounds[i];
+            const uint32_t nb = BUCKET == BK_HIST ? (uint32_t)p.dom_size : p.side_dom;
+            for (uint32_t i = tid; i <= nb; i += blockDim.x) b[i] = p.hist_bounds[i];
         }
     }
     __syncthreads();
@@ -409,13 +419,9 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
             for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
 
-            // every f64 column this tile touches is non-negative (min_value's sign bit): code -> f64 is one XOR
-            bool fpos = true;
-            if (BUCKET == BK_HIST || BUCKET == BK_RANK) fpos = fpos && (kc.minhi >> 31);
-#pragma unroll
-            for (int g = 0; g < NBG; g++) fpos = fpos && (p.bgroups[g].kind != TAGG_F64 || (bc[g].minhi >> 31));
-#pragma unroll
-            for (int g = 0; g < NRG; g++) fpos = fpos && (p.rgroups[g].kind != TAGG_F64 || (rc[g].minhi >> 31));
+            // every f64 column this tile touches lies in [+0.0, +inf] (host-checked against the column headers):
+            // code -> f64 is one XOR, and f64 min / max agree with the order of the codes
+            const bool fpos = (flags & SF_FPOS) != 0;
             uint64_t rbase = 0;  // CT root: f64 bits = delta + rbase when fpos
             if (CTROOT) {
                 const uint64_t mv = ((uint64_t)rc[0].minhi << 32) | rc[0].minlo;
@@ -423,10 +429,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 rbase = mv ^ 0x8000000000000000ull;
             }
             // histogram: ordinal via multiply + boundary fix-up (exact), see SParams::hist_bounds
-            const bool hb = BUCKET == BK_HIST && p.hist_bounds != nullptr;
+            const bool hb = (BUCKET == BK_HIST || BUCKET == BK_RANK) && p.hist_bounds != nullptr;
             const uint32_t hb_saddr = smem_saddr + p.soff_hist_bounds;
+            const uint32_t hb_dom = BUCKET == BK_HIST ? dom_size32 : p.side_dom;
             uint64_t hb_first = 0, hb_end = 0;
-            if (hb) { hb_first = lds64(hb_saddr); hb_end = lds64(hb_saddr + 8 * dom_size32); }
+            if (hb) { hb_first = lds64(hb_saddr); hb_end = lds64(hb_saddr + 8 * hb_dom); }
+            const double hb_dmin = (double)(BUCKET == BK_HIST ? p.dom_min : p.side_dom_min);
 
             auto flush_tail = [&]() {  // warp-uniform: wtail buffered codes -> the global list
                 __syncwarp();
@@ -454,6 +462,19 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 constexpr bool CHECK = decltype(CHECK_)::value;
                 constexpr bool POS = decltype(POS_)::value;
                 auto c2f = [](uint64_t code) { return POS ? __longlong_as_double((long long)(code ^ 0x8000000000000000ull)) : code_to_f64(code); };
+                // histogram ordinal of a code relative to the first bucket, -1: skipped (NaN or below start, histogram.rs:138-145).
+                // A multiply lands next to the exact ordinal; the boundary table (exact, monotone in the code) decides.
+                auto hist_bin = [&](uint64_t code) -> int {
+                    const double t = __dsub_rn(__dmul_rn(__dsub_rn(c2f(code), p.f0), p.hist_inv), hb_dmin);
+                    uint32_t r = (uint32_t)min(max(__double2int_rz(t), 0), (int)hb_dom - 1);
+                    const uint64_t b0 = lds64(hb_saddr + 8 * r), b1 = lds64(hb_saddr + 8 * r + 8);
+                    if (code < b0 || code >= b1) {
+                        if (code < hb_first || code >= hb_end) return -1;
+                        while (code < lds64(hb_saddr + 8 * r)) r--;
+                        while (code >= lds64(hb_saddr + 8 * (r + 1))) r++;
+                    }
+                    return (int)r;
+                };
                 bool act[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) { act[u] = CHECK ? act_in[u] : true; rseen = rseen || act[u]; }
@@ -515,20 +536,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
                                 tail[u] = d >= p.rank_span;
                                 tail_code[u] = code;
-                            } else if (hb) {
-                                // NaN or below start lie outside [hb_first, hb_end): skipped (histogram.rs:138-145)
-                                const uint64_t code = tget(kc, dl[u]);
-                                if (code < hb_first || code >= hb_end) {
-                                    act[u] = false;
-                                } else {
-                                    const double t = __dmul_rn(__dsub_rn(c2f(code), p.f0), p.hist_inv);
-                                    long long j = (long long)t - (long long)p.dom_min;  // near the exact ordinal; the table decides
-                                    j = j < 0 ? 0 : (j >= (long long)dom_size32 ? (long long)dom_size32 - 1 : j);
-                                    uint32_t r = (uint32_t)j;
-                                    while (code < lds64(hb_saddr + 8 * r)) r--;
-                                    while (code >= lds64(hb_saddr + 8 * (r + 1))) r++;
-                                    rel[u] = r;
+                                if (hb) {  // the fused histogram counts every matched value, binned or not
+                                    const int r = hist_bin(code);
+                                    if (r >= 0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_side_count + 4 * (uint32_t)r) : "memory");
                                 }
+                            } else if (hb) {
+                                const int r = hist_bin(tget(kc, dl[u]));
+                                if (r < 0) act[u] = false;
+                                else rel[u] = (uint32_t)r;
                             } else {
                                 uint64_t ord;
                                 // NaN or below start: skipped (histogram.rs:138-145)
@@ -743,6 +758,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x)
             if ((bm[i >> 5] >> (i & 31)) & 1u) p.present_out[i] = 1;
     }
+    if (BUCKET == BK_RANK && p.side_dom) {
+        __syncthreads();
+        const uint32_t* sc = (const uint32_t*)(smem + p.soff_side_count);
+        for (uint32_t i = tid; i < p.side_dom; i += blockDim.x) {
+            const uint32_t v = sc[i];
+            if (v) { atomicAdd((unsigned long long*)(p.side_count_acc + i), (unsigned long long)v); p.side_present[i] = 1; }
+        }
+    }
     if (STAB) {
         // merge the CTA's private tables into the global ones; count table 0 always exists in STAB mode
         // (hidden when the plan has no count) and is the record of which buckets exist
@@ -852,6 +875,9 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
             case OPB_MIN: return pick_ct_root<OPB_MIN>(compact);
             case OPB_MAX: return pick_ct_root<OPB_MAX>(compact);
             case OPB_SUM: return pick_ct_root<OPB_SUM>(compact);
+            case OPB_MIN | OPB_MAX: return pick_ct_root<(OPB_MIN | OPB_MAX)>(compact);
+            case OPB_MIN | OPB_SUM: return pick_ct_root<(OPB_MIN | OPB_SUM)>(compact);
+            case OPB_MAX | OPB_SUM: return pick_ct_root<(OPB_MAX | OPB_SUM)>(compact);
             case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_root<(OPB_MIN | OPB_MAX | OPB_SUM)>(compact);
         }
     }
@@ -866,6 +892,55 @@ static bool j_monotone(const std::vector<uint64_t>& b) {
     for (size_t i = 1; i < b.size(); i++)
         if (b[i] < b[i - 1]) return false;
     return true;
+}
+
+// hist_bounds[j] = smallest code c <= code(+inf) that is not skipped and whose ordinal is >= dom_min + j (code(+inf) + 1
+// if none), j = 0..dom_size.  The exact expression floor((k - start) / interval) (histogram.rs:146) is monotone in the
+// order-preserving code, so each boundary is found by a local search around code(start + o * interval).
+static bool hist_boundaries(double start, double interval, uint64_t dom_min, uint64_t dom_size, std::vector<uint64_t>& B) {
+    const uint64_t top = f64_to_code_h(INFINITY);
+    auto reaches = [&](uint64_t c, uint64_t o) { uint64_t ord; return c <= top && hist_ord_h(c, start, interval, &ord) && ord >= o; };
+    B.assign(dom_size + 1, 0);
+    for (uint64_t j = 0; j <= dom_size; j++) {
+        const uint64_t o = dom_min + j;
+        if (!reaches(top, o)) { B[j] = top + 1; continue; }
+        uint64_t g = f64_to_code_h(start + (double)o * interval);
+        if (g > top) g = top;
+        uint64_t lo, hi;  // !reaches(lo), reaches(hi)
+        if (reaches(g, o)) {
+            hi = g;
+            lo = g;
+            uint64_t step = 1;
+            bool bottom = false;
+            while (true) {
+                if (lo < step) { bottom = true; break; }
+                lo -= step;
+                if (!reaches(lo, o)) break;
+                hi = lo;
+                step <<= 1;
+            }
+            if (bottom) {
+                if (reaches(0, o)) { B[j] = 0; continue; }
+                lo = 0;
+            }
+        } else {
+            lo = g;
+            hi = g;
+            uint64_t step = 1;
+            while (true) {
+                hi = top - hi < step ? top : hi + step;
+                if (reaches(hi, o)) break;
+                lo = hi;
+                step <<= 1;
+            }
+        }
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (reaches(mid, o)) hi = mid; else lo = mid;
+        }
+        B[j] = hi;
+    }
+    return j_monotone(B);
 }
 
 struct Shape {
@@ -982,9 +1057,14 @@ static int stream_launch(ExecState& es, bool first_launch) {
     } else {
         members.push_back(node);
     }
+    // percentiles first: a histogram over the same column can ride along in that pass
+    std::stable_sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) {
+        return (m.nodes[a].op == TAGG_OP_PERCENTILES) > (m.nodes[b].op == TAGG_OP_PERCENTILES);
+    });
     std::vector<uint32_t> covered;
     for (uint32_t mem : members) {
         if (es.skip[mem]) continue;  // handled by an earlier launch
+        if (std::find(covered.begin(), covered.end(), mem) != covered.end()) continue;  // fused into another member's pass
         const tagg_node& nd = m.nodes[mem];
         if (nd.op == TAGG_OP_COUNT) {
             if (!first_launch || sp.n_root_counts >= 2) continue;
@@ -1025,6 +1105,22 @@ static int stream_launch(ExecState& es, bool first_launch) {
             G.acc_min = R.d_min;
             G.acc_max = R.d_max;
             covered.push_back(mem);
+            // histogram_agg_f64(same column, interval, count_agg()) in the same tuple: fused (BASELINE config C3)
+            for (uint32_t h : members) {
+                const tagg_node& hn = m.nodes[h];
+                if (es.skip[h] || hn.op != TAGG_OP_HISTOGRAM || hn.multi || m.col_slot[h] != m.col_slot[mem]) continue;
+                const ScopeLayout& HL = es.scopes[m.own_scope[h]];
+                if (HL.mode != SCOPE_DENSE || HL.dom_size > 256 || HL.capacity != HL.dom_size) continue;
+                if (m.end[h] != h + 2 || m.nodes[h + 1].op != TAGG_OP_COUNT) continue;
+                sp.side_dom = (uint32_t)HL.dom_size;
+                sp.side_dom_min = HL.dom_min;
+                sp.f0 = hn.f0;
+                sp.f1 = hn.f1;
+                sp.side_count_acc = (uint64_t*)(es.arena + es.slots[m.slot_of[h + 1]].off_acc);
+                sp.side_present = es.arena + HL.off_present;
+                covered.push_back(h);
+                break;
+            }
         } else if (nd.op == TAGG_OP_TERMS || nd.op == TAGG_OP_HISTOGRAM) {
             if (bucket_mode != BK_NONE || nd.multi) continue;  // one bucket node per launch; multi-valued: generic kernel
             const int sc = m.own_scope[mem];
@@ -1104,6 +1200,14 @@ static int stream_launch(ExecState& es, bool first_launch) {
             d.nb[c] = col.num_bits;
             d.minv[c] = col.min_value;
         }
+        {
+            bool fpos = true;
+            for (int c = 0; c < sp.n_cols; c++) {
+                const DevColumn& col = hs.cols[sh.staged[c]];
+                if (col.kind == TAGG_F64 && col.n_values && (col.min_value < 0x8000000000000000ull || col.max_value > 0xFFF0000000000000ull)) fpos = false;
+            }
+            if (fpos) d.flags |= SF_FPOS;
+        }
         if (hs.main.kind == DS_BITSET) { d.flags |= SF_MAIN_BITS; d.bits_ptr[0] = (const uint8_t*)hs.main.words; narrowing = true; }
         if (hs.has_deletes) { d.flags |= SF_DELETES; d.bits_ptr[1] = (const uint8_t*)hs.deleted; narrowing = true; }
         for (int pi = 0; pi < sp.n_preds; pi++) {
@@ -1162,60 +1266,28 @@ static int stream_launch(ExecState& es, bool first_launch) {
         }
         if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
     }
-    // histogram with few buckets: exact code boundaries of the ordinals (host: a guess from start + o * interval,
-    // then a local search on the exact IEEE expression, which is monotone in the code)
-    if (bucket_mode == BK_HIST && stab && sp.dom_size <= 256 && tiles_total >= 2048) {
-        const double start = sp.f0, interval = sp.f1;
-        const uint64_t top = f64_to_code_h(INFINITY);
-        auto reaches = [&](uint64_t c, uint64_t o) { uint64_t ord; return c <= top && hist_ord_h(c, start, interval, &ord) && ord >= o; };
-        std::vector<uint64_t> B(sp.dom_size + 1);
-        bool ok = true;
-        for (uint64_t j = 0; j <= sp.dom_size && ok; j++) {
-            const uint64_t o = sp.dom_min + j;
-            // smallest code c <= top with reaches(c, o); top + 1 if none
-            if (!reaches(top, o)) { B[j] = top + 1; continue; }
-            uint64_t g = f64_to_code_h(start + (double)o * interval);
-            if (g > top) g = top;
-            uint64_t lo, hi;  // invariant: !reaches(lo) (or lo == 0 unknown), reaches(hi)
-            if (reaches(g, o)) {
-                hi = g;
-                uint64_t step = 1;
-                lo = g;
-                while (true) {
-                    if (lo < step) { lo = 0; break; }
-                    lo -= step;
-                    if (!reaches(lo, o)) break;
-                    hi = lo;
-                    step <<= 1;
-                }
-                if (lo == 0 && reaches(0, o)) { B[j] = 0; continue; }
-            } else {
-                lo = g;
-                uint64_t step = 1;
-                hi = g;
-                while (true) {
-                    hi = top - hi < step ? top : hi + step;
-                    if (reaches(hi, o)) break;
-                    lo = hi;
-                    step <<= 1;
-                }
+    // histogram with few buckets (the launch's bucket node, or the one fused into a percentile pass): exact code
+    // boundaries of the ordinals
+    {
+        const bool own = bucket_mode == BK_HIST && stab && sp.dom_size <= 256 && tiles_total >= 2048;
+        const bool side = bucket_mode == BK_RANK && sp.side_dom > 0;
+        if (own || side) {
+            std::vector<uint64_t> B;
+            const uint64_t hdom_min = own ? sp.dom_min : sp.side_dom_min, hdom = own ? sp.dom_size : sp.side_dom;
+            if (hist_boundaries(sp.f0, sp.f1, hdom_min, hdom, B)) {
+                uint64_t* d_b = nullptr;
+                if (cudaMallocAsync((void**)&d_b, B.size() * 8, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "histogram boundary table allocation failed");
+                es.temps.push_back(d_b);
+                if (cudaMemcpyAsync(d_b, es.pin(B.data(), B.size() * 8), B.size() * 8, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
+                    return -tagg_fail(TAGG_ERR_CUDA, "histogram boundary table upload failed");
+                sp.hist_bounds = d_b;
+                sp.hist_inv = 1.0 / sp.f1;
+                sp.soff_hist_bounds = (uint32_t)table_bytes;
+                table_bytes += (B.size() * 8 + 127) & ~(size_t)127;
+                if (side) { sp.soff_side_count = (uint32_t)table_bytes; table_bytes += ((size_t)sp.side_dom * 4 + 127) & ~(size_t)127; }
+            } else if (side) {
+                return -tagg_fail(TAGG_ERR_CUDA, "histogram boundaries are not monotone (internal error)");
             }
-            while (hi - lo > 1) {
-                const uint64_t mid = lo + (hi - lo) / 2;
-                if (reaches(mid, o)) hi = mid; else lo = mid;
-            }
-            B[j] = hi;
-        }
-        if (j_monotone(B)) {
-            uint64_t* d_b = nullptr;
-            if (cudaMallocAsync((void**)&d_b, B.size() * 8, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "histogram boundary table allocation failed");
-            es.temps.push_back(d_b);
-            if (cudaMemcpyAsync(d_b, es.pin(B.data(), B.size() * 8), B.size() * 8, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
-                return -tagg_fail(TAGG_ERR_CUDA, "histogram boundary table upload failed");
-            sp.hist_bounds = d_b;
-            sp.hist_inv = 1.0 / interval;
-            sp.soff_hist_bounds = (uint32_t)table_bytes;
-            table_bytes += (B.size() * 8 + 127) & ~(size_t)127;
         }
     }
     // global tables that no count names: bucket existence through a CTA bitmap in shared memory
@@ -1225,10 +1297,15 @@ static int stream_launch(ExecState& es, bool first_launch) {
     }
     uint32_t n_groups = 1, n_stages = 3;
     if (stab) {
-        const uint32_t cand[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
+        // more consumer warps beat a deeper ring (measured on C3: 3 groups x 2 stages 2.08 ms, 2 x 3 2.58 ms)
+        const uint32_t cand[][2] = {{3, 4}, {3, 3}, {3, 2}, {2, 4}, {2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
         bool ok = false;
         for (auto& c : cand)
             if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
+        if (const char* ov = getenv("TAGG_STREAM_GS")) {  // experiment: "groups,stages"
+            uint32_t g = 0, st = 0;
+            if (sscanf(ov, "%u,%u", &g, &st) == 2 && g >= 1 && g <= ST_MAXGROUPS && st >= 2 && st <= ST_MAXSTAGES && table_bytes + g * group_bytes(st) <= SMEM_MAX) { n_groups = g; n_stages = st; }
+        }
         if (!ok) { stab = false; table_bytes = 0; sp.hist_bounds = nullptr; }
     }
     if (bucket_mode == BK_RANK && !stab) return -tagg_fail(TAGG_ERR_CUDA, "rank-bin tables do not fit shared memory (internal sizing error)");
