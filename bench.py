@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 STATUS, CATEGORY, PRICE = 0, 1, 2
 TAG_STATUS, TAG_CATEGORY, TAG_PRICE = 11, 22, 33
 SEED = 1
-N_CATEGORIES = 10_000
+N_CATEGORIES = int(os.environ.get("TAGG_BENCH_NCAT", "10000"))  # 10k = BASELINE config C2
 METRIC = "matched docs aggregated/sec"
 UNIT = "docs/s"
 
