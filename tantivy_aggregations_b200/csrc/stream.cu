@@ -115,6 +115,12 @@ struct SParams {
     uint64_t side_dom_min;
     uint64_t* side_count_acc;
     uint8_t* side_present;
+    // global tables (too many buckets for shared tables) with min / max on bucket group 0: one byte per bucket in shared
+    // memory holds the best 4-bit LEVEL seen by this CTA — level = (code - nib_lo) >> nib_shift clamped to 15, high nibble
+    // for max, low nibble (15 - level) for min.  Only values whose level reaches the filter touch the global cells (a
+    // fire-and-forget RED); updates of the byte are plain stores (a lost update only weakens the filter)
+    uint32_t soff_nib, nib_shift;
+    uint64_t nib_lo;
     uint32_t soff_present_bits;  // global tables without a count: CTA bitmap of touched buckets (0 = none), flushed at the end
     uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
     uint8_t* present_out;  // STAB: written by the final table merge
@@ -394,6 +400,44 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
                     const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
                     const uint8_t* lut = p.pred_lut[i];
+                    if (pc.nb >= 1 && pc.nb <= 8 && (type == PR_RANGE || hi <= 32)) {
+                        // Narrow column (status-like fields): lane l tests documents [8l, 8l + 8) of the warp's 256 from one
+                        // 64-bit window of the packed stream, on the packed deltas (the predicate's code range is moved
+                        // into the delta domain once per tile; a LUT of <= 32 entries lives in a register), then the
+                        // result bytes are regrouped into the word-per-lane layout.  ~4x fewer instructions than a
+                        // ballot per 32 documents.
+                        const uint64_t minv = ((uint64_t)pc.minhi << 32) | pc.minlo;
+                        const uint64_t last = type == PR_LUT ? lo + hi - 1 : hi;  // last code that can pass (LUT: hi = entries > 0 here)
+                        uint32_t vlo = 1, vspan = 0, roff = 0, lutw = 0xffffffffu;  // empty unless set below
+                        bool any = type == PR_LUT ? hi > 0 && last >= lo : hi >= lo;
+                        any = any && last >= minv && lo <= minv + 255;
+                        if (any) {
+                            vlo = lo > minv ? (uint32_t)(lo - minv) : 0u;
+                            const uint32_t vhi = last - minv > 255 ? 255u : (uint32_t)(last - minv);
+                            vspan = vhi - vlo;
+                            if (type == PR_LUT) {
+                                roff = (uint32_t)(minv + vlo - lo);  // LUT index of delta vlo
+                                lutw = (uint32_t)lut[0] | ((uint32_t)lut[1] << 8) | ((uint32_t)lut[2] << 16) | ((uint32_t)lut[3] << 24);
+                            }
+                        }
+                        const uint32_t B = (warp * 32 + lane) * pc.nb;  // byte offset of this lane's 8 values
+                        const uint32_t a = pc.saddr + (B & ~3u), sh = (B & 3u) * 8;
+                        const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
+                        const uint64_t win = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+                        uint32_t okb = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const uint32_t t = ((uint32_t)(win >> (k * pc.nb)) & pc.mlo) - vlo;  // delta - vlo, wraps below
+                            const bool ok = any && t <= vspan && ((lutw >> ((t + roff) & 31u)) & 1u);
+                            okb |= ok ? (1u << k) : 0u;
+                        }
+                        // word j of the warp = bytes of lanes 4j .. 4j + 3
+                        uint32_t pm = 0;
+#pragma unroll
+                        for (int t = 0; t < 4; t++) pm |= __shfl_sync(0xffffffffu, okb, (lane * 4 + t) & 31) << (8 * t);
+                        m &= pm;
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < ST_WORDS_PER_WARP; j++) {
                         uint32_t mj = __shfl_sync(0xffffffffu, m, j);
@@ -599,15 +643,21 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         const SGroup& G = p.bgroups[g];
                         const uint32_t ops = g == 0 ? ops_b0 : g == 1 ? ops_b1 : ops_b2;
                         uint64_t code[U], cur_min[U], cur_max[U];
+                        const bool nibf = !STAB && g == 0 && p.soff_nib != 0;
+                        uint32_t nfb[U], nq[U];
                         // min / max cells: read all U of them first.  STAB: the CTA's shared table.  Otherwise
                         // global: a plain (L1, possibly stale) read filters most documents, survivors are
                         // confirmed at L2 before the atomic.
 #pragma unroll
                         for (int u = 0; u < U; u++) {
-                            code[u] = 0; cur_min[u] = ~0ull; cur_max[u] = ~0ull;
+                            code[u] = 0; cur_min[u] = ~0ull; cur_max[u] = ~0ull; nfb[u] = 0; nq[u] = 0;
                             if (act[u]) {
                                 code[u] = BUCKET == BK_RANK ? tail_code[u] : tget(bc[g], dl[u]);
-                                if (filt) {
+                                if (nibf) {
+                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(nfb[u]) : "r"(smem_saddr + p.soff_nib + rel[u]));
+                                    const uint64_t lv = code[u] >= p.nib_lo ? (code[u] - p.nib_lo) >> p.nib_shift : 0ull;
+                                    nq[u] = lv > 15 ? 15u : (uint32_t)lv;
+                                } else if (filt) {
                                     if (ops & OPB_MIN) cur_min[u] = (uint64_t)lds32(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]) << 32;
                                     if (ops & OPB_MAX) cur_max[u] = (uint64_t)lds32(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]) << 32;
                                 } else {
@@ -623,6 +673,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                     uint64_t* a = STAB ? (uint64_t*)(smem + p.soff_tab_sum[g]) + rel[u] : G.acc_sum + rel[u];
                                     if (G.kind == TAGG_F64) atomicAdd((double*)a, c2f(code[u]));
                                     else atomicAdd((unsigned long long*)a, (unsigned long long)code_to_bits(G.kind, code[u]));
+                                }
+                                if (nibf) {
+                                    const uint32_t fx = nfb[u] >> 4, fn = nfb[u] & 15u, qx = nq[u], qn = 15u - nq[u];
+                                    uint32_t nx = fx, nn = fn;
+                                    if ((ops & OPB_MAX) && qx >= fx) { atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]); nx = qx; }
+                                    if ((ops & OPB_MIN) && qn >= fn) { atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]); nn = qn; }
+                                    if (nx != fx || nn != fn) asm volatile("st.shared.u8 [%0], %1;" ::"r"(smem_saddr + p.soff_nib + rel[u]), "r"((nx << 4) | nn) : "memory");
+                                    continue;
                                 }
                                 if ((ops & OPB_MIN) && cur_min[u] < ~code[u]) {
                                     if (filt) {  // fire-and-forget: no load sits between the filter and the global RED
@@ -1337,7 +1395,36 @@ static int stream_launch(ExecState& es, bool first_launch) {
         sp.soff_present_bits = 128;
         table_bytes = 128 + ((((size_t)sp.dom_size + 31) / 32 * 4 + 127) & ~(size_t)127);
     }
+    // global tables with min / max on the first bucket group: 4-bit level filter in shared memory (see SParams::soff_nib)
+    bool nib = false;
+    static const bool no_nib = getenv("TAGG_NO_NIB") != nullptr;  // experiment switch
+    if (!no_nib && bucket_mode == BK_TERMS && !stab && n_bgroups >= 1 && (sp.bgroups[0].ops & (OPB_MIN | OPB_MAX)) && sp.dom_size <= 160 * 1024) {
+        uint64_t glo = ~0ull, ghi = 0;
+        for (auto& hs : es.hsegs) {
+            const DevColumn& col = hs.cols[sh.staged[sp.bgroups[0].scol]];
+            if (!col.n_values) continue;
+            glo = std::min(glo, col.min_value);
+            ghi = std::max(ghi, col.max_value);
+        }
+        if (glo <= ghi) {
+            const uint64_t span = ghi - glo;
+            const uint32_t bits = span ? 64 - (uint32_t)__builtin_clzll(span) : 0;
+            sp.nib_lo = glo;
+            sp.nib_shift = bits > 4 ? bits - 4 : 0;
+            if (table_bytes == 0) table_bytes = 128;
+            sp.soff_nib = (uint32_t)table_bytes;
+            table_bytes += ((size_t)sp.dom_size + 127) & ~(size_t)127;
+            nib = true;
+        }
+    }
     uint32_t n_groups = 1, n_stages = 3;
+    if (nib) {  // tables are per CTA: one CTA per SM with as many consumer groups as fit
+        const uint32_t cand[][2] = {{3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 3}, {1, 2}};
+        bool ok = false;
+        for (auto& c : cand)
+            if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
+        if (!ok) { nib = false; sp.soff_nib = 0; table_bytes = sp.soff_present_bits ? 128 + ((((size_t)sp.dom_size + 31) / 32 * 4 + 127) & ~(size_t)127) : 0; }
+    }
     if (stab) {
         // more consumer warps beat a deeper ring (measured on C3: 3 groups x 2 stages 2.08 ms, 2 x 3 2.58 ms)
         const uint32_t cand[][2] = {{3, 4}, {3, 3}, {3, 2}, {2, 4}, {2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
@@ -1351,7 +1438,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
         if (!ok) { stab = false; table_bytes = 0; sp.hist_bounds = nullptr; sp.tab_filt = 0; }
     }
     if (bucket_mode == BK_RANK && !stab) return -tagg_fail(TAGG_ERR_CUDA, "rank-bin tables do not fit shared memory (internal sizing error)");
-    if (!stab) {
+    if (!stab && !nib) {
         // one group per CTA, several CTAs per SM: take the ring depth that keeps the most consumer warps resident
         n_groups = 1;
         if (table_bytes + group_bytes(2) > SMEM_MAX) return 0;
