@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-segments", type=int, default=8, help="segments of the workload the CPU baseline runs on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 force generic kernel, 2 force streaming kernel")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, the bench contract's workload, weak scaling) | c5: BASELINE configs[4], 1B docs in 64 segments "
+                         "sharded over the ranks, post_filter + terms + nested min/max/sum, NCCL bucket merge (strong scaling)")
     return ap.parse_args()
 
 
@@ -367,10 +370,126 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[4] (C5): 1B docs / 64 segments sharded over the ranks, strong scaling.  Not the bench
+# contract's workload (that is C2 above); run by hand for the scaling table in DESIGN.md / profiles/.
+# ---------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    import tantivy_aggregations_b200 as ta
+    from tantivy_aggregations_b200 import _ffi as F
+    from tantivy_aggregations_b200 import index as I
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = ta.Context(local_rank)
+    if world > 1:
+        ident = [ta.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        ctx.comm_init(ident[0], rank, world)
+    n_total, n_seg, n_cat = 1_000_000_000, 64, 100_000
+    per_seg = n_total // n_seg
+    mine = ta.assign_segments([per_seg] * n_seg, world)[rank]
+    segments = []
+    for s in mine:
+        seg = ta.Segment(ctx, per_seg, keep_host=False)
+        seg.synth_column(STATUS, ta.U64, 1, SEED, TAG_STATUS, s * per_seg, 0, 4)
+        seg.synth_column(CATEGORY, ta.U64, 1, SEED, TAG_CATEGORY, s * per_seg, 1, n_cat)
+        seg.synth_column(PRICE, ta.F64, 0, SEED, TAG_PRICE, s * per_seg)
+        segments.append(seg)
+    searcher = ta.Searcher(ctx, segments)
+    agg = ta.post_filter_agg_u64(STATUS, ta.eq(0), ta.terms_agg_u64(CATEGORY, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_f64(PRICE))))
+    plan = searcher.prepare(agg)
+    terms = agg.sub
+    nodes = [m.node for m in terms.sub.members]
+    allq = ta.AllQuery()
+    lib = F.lib()
+    run = lib.tagg_execute_collective if world > 1 else lib.tagg_execute
+
+    def step():
+        arr, keep = I.build_inputs(plan, allq, segments)
+        h = C.c_void_p()
+        F.check(run(plan._h, arr, len(segments), C.byref(h)))
+        reader = I.ResultReader(h)
+        keys, parents = reader.scope(terms.node)
+        nbytes = keys.nbytes + parents.nbytes
+        vals = []
+        for nd in nodes:
+            v, sflag = reader.metric(nd)
+            nbytes += v.nbytes + sflag.nbytes
+            vals.append(v)
+        st = reader.stats()
+        reader.free()
+        return keys, vals, nbytes, st
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    keys, vals, _, _ = step()
+    assert len(keys) == n_cat, len(keys)
+    mn, mx = vals[0].view(np.float64), vals[1].view(np.float64)
+    assert (mn >= 1.0).all() and (mx < 101.0).all() and (mn <= mx).all()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    ctx.timer_start()
+    kernel_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        _, _, nbytes, st = step()
+        kernel_ms += st["kernel_ms"]
+        launches += st["n_launches"]
+    ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    alg = st["alg_bytes"]
+    if dist is not None:
+        t = torch.tensor([ms, kernel_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kernel_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg / (kernel_ms / args.steps * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64/f64", "data": "synthetic",
+            "config": {"workload": "C5 post_filter_agg_u64(status==0, terms_u64(category 100k, (min,max,sum f64 price))) AllQuery, 1e9 docs in 64 segments "
+                                   f"sharded over {world} GPU(s)", "l2": "inputs (>= 1.16 GB per GPU and step) are larger than the 126 MB L2",
+                       "multi_gpu": "bucket tables merged by NCCL every step" if world > 1 else "single GPU"},
+            "kernel_ms_per_step": kernel_ms / args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_stream", "algorithmic_bytes_per_launch": alg, "note": "per GPU (slowest rank)"},
+            "e2e": {"value": n_total * args.steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": nbytes,
+                    "note": "the query has no host docset (post_filter on a fast field); result arrays are read back every step"},
+            "gpu_launches": launches, "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+        }))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_b200(args)
 

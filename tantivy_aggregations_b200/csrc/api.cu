@@ -56,7 +56,7 @@ CallRes* tagg_ctx::acquire_call() {
     cudaEventCreate(&c->ev1);
     for (auto& e : c->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming);
-    c->pinned_bytes = 1 << 20;
+    c->pinned_bytes = 8 << 20;  // arenas up to this size come back whole in one pinned copy
     if (cudaHostAlloc((void**)&c->pinned, c->pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
         c->pinned = nullptr;
         c->pinned_bytes = 0;

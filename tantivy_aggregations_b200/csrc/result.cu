@@ -39,7 +39,8 @@ static int fetch(ExecState& es, const T* d_src, uint64_t capacity, const std::ve
     if (raw.empty()) return 0;
     if (es.host_arena) {  // the whole arena is already on the host
         const T* h = (const T*)(es.host_arena + ((const uint8_t*)d_src - es.arena));
-        for (size_t i = 0; i < raw.size(); i++) out[i] = h[raw[i]];
+        if (raw.size() == capacity) memcpy(out.data(), h, capacity * sizeof(T));  // every bucket exists: raw is the identity
+        else for (size_t i = 0; i < raw.size(); i++) out[i] = h[raw[i]];
         return 0;
     }
     if (capacity <= FULL_COPY_MAX) {
@@ -157,8 +158,11 @@ int read_result(ExecState& es, tagg_result* res) {
                 CUDA_TRY(cudaStreamSynchronize(es.st));
                 present = present_copy.data();
             }
-            raw[s].reserve(4096);
-            {   // 8 flags at a time: most of a big table is empty
+            raw[s].reserve(L.capacity <= (1u << 20) ? (size_t)L.capacity : 4096);
+            if (L.capacity && !memchr(present, 0, L.capacity)) {  // every bucket exists
+                raw[s].resize(L.capacity);
+                for (uint64_t i = 0; i < L.capacity; i++) raw[s][i] = (uint32_t)i;
+            } else {   // 8 flags at a time: most of a big table is empty
                 uint64_t i = 0;
                 for (; i + 8 <= L.capacity; i += 8) {
                     uint64_t w;
@@ -230,14 +234,21 @@ int read_result(ExecState& es, tagg_result* res) {
         if (rc) return rc;
         rc = fetch<uint8_t>(es, es.arena + SL.off_seen, SL.capacity, raw[s], d_raw[s], R.seen);
         if (rc) return rc;
-        for (size_t i = 0; i < R.values.size(); i++) {
-            switch (nd.op) {
-                case TAGG_OP_COUNT: R.seen[i] = 1; break;
-                case TAGG_OP_SUM: break;  // accumulated in the natural type already
-                case TAGG_OP_MIN: R.values[i] = R.seen[i] ? code_to_bits_h(nd.kind, ~R.values[i]) : 0; break;
-                case TAGG_OP_MAX: R.values[i] = R.seen[i] ? code_to_bits_h(nd.kind, R.values[i]) : 0; break;
-            }
-            if (!R.seen[i] && nd.op != TAGG_OP_COUNT) R.values[i] = 0;
+        const size_t nv = R.values.size();
+        uint64_t* V = R.values.data();
+        uint8_t* Sn = R.seen.data();
+        const int kind = nd.kind;
+        switch (nd.op) {
+            case TAGG_OP_COUNT: memset(Sn, 1, nv); break;
+            case TAGG_OP_SUM:  // accumulated in the natural type already
+                for (size_t i = 0; i < nv; i++) if (!Sn[i]) V[i] = 0;
+                break;
+            case TAGG_OP_MIN:
+                for (size_t i = 0; i < nv; i++) V[i] = Sn[i] ? code_to_bits_h(kind, ~V[i]) : 0;
+                break;
+            case TAGG_OP_MAX:
+                for (size_t i = 0; i < nv; i++) V[i] = Sn[i] ? code_to_bits_h(kind, V[i]) : 0;
+                break;
         }
     }
     lap("slots");

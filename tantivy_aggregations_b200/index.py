@@ -356,8 +356,8 @@ class ResultReader:
         if node not in self._scopes:
             n = C.c_uint64()
             F.check(F.lib().tagg_result_scope_len(self._h, node, C.byref(n)))
-            keys = np.zeros(n.value, dtype=np.uint64)
-            parents = np.zeros(n.value, dtype=np.uint32)
+            keys = np.empty(n.value, dtype=np.uint64)
+            parents = np.empty(n.value, dtype=np.uint32)
             F.check(F.lib().tagg_result_scope_read(self._h, node, _ptr(keys), _ptr(parents), n.value))
             self._scopes[node] = (keys, parents)
         return self._scopes[node]
@@ -379,8 +379,8 @@ class ResultReader:
     def metric(self, node):
         if node not in self._metrics:
             n = self._metric_len(node)
-            values = np.zeros(n, dtype=np.uint64)
-            seen = np.zeros(n, dtype=np.uint8)
+            values = np.empty(n, dtype=np.uint64)
+            seen = np.empty(n, dtype=np.uint8)
             F.check(F.lib().tagg_result_metric_read(self._h, node, _ptr(values), _ptr(seen), n))
             self._metrics[node] = (values, seen)
         return self._metrics[node]
