@@ -33,6 +33,12 @@ if "c1" in which:
 if "c1x" in which:
     segs = segs_of(1_000_000_000, 64, [price]); run("C1 x1000 (1G docs)", ta.Searcher(ctx, segs), ta.AllQuery(), c1agg)
     for s in segs: s.close()
+if "c3pair" in which:  # only the fused (histogram, percentiles) tuple — the ncu target
+    segs = segs_of(500_000_000, 8, [price]); S = ta.Searcher(ctx, segs)
+    rng = np.random.default_rng(3)
+    q = ta.CachedQuery(ta.BitsetQuery({i: rng.integers(0, 256, size=(s.max_doc + 7) // 8, dtype=np.uint8) for i, s in enumerate(segs)}), segs)
+    run("C3 (hist, percentiles) 500M/50%", S, q, lambda: (ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)), reps=3)
+    for s in segs: s.close()
 if "c3" in which:
     segs = segs_of(500_000_000, 8, [price]); S = ta.Searcher(ctx, segs)
     rng = np.random.default_rng(3)
