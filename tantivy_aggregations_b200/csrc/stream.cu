@@ -179,6 +179,7 @@ struct TileDesc {
     uint32_t nb[ST_MAXCOLS];
     uint64_t minv[ST_MAXCOLS];
     uint64_t pred_lo[ST_MAXPRED], pred_hi[ST_MAXPRED];
+    uint32_t seg, pad;  // segment of the tile: consumers rebuild their column descriptors only when it changes
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -199,7 +200,8 @@ struct TCol {
 #define TD_MINV(c) (8 + 4 * ST_MAXCOLS + 8 * (c))
 #define TD_PRED_LO(i) (8 + 12 * ST_MAXCOLS + 8 * (i))
 #define TD_PRED_HI(i) (8 + 12 * ST_MAXCOLS + 8 * ST_MAXPRED + 8 * (i))
-static_assert(sizeof(TileDesc) == 8 + 12 * ST_MAXCOLS + 16 * ST_MAXPRED, "TileDesc layout");
+#define TD_SEG (8 + 12 * ST_MAXCOLS + 16 * ST_MAXPRED)
+static_assert(sizeof(TileDesc) == 16 + 12 * ST_MAXCOLS + 16 * ST_MAXPRED, "TileDesc layout");
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     uint64_t v;
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             } else if (lane == 16) {
                 T->n_valid = (uint32_t)min((uint64_t)ST_TILE, (uint64_t)Sg->max_doc - (uint64_t)lt * ST_TILE);
                 T->flags = flags;
+                T->seg = cur_seg;
             } else if (lane >= 17 && lane < 17 + ST_MAXCOLS) {
                 uint32_t c = lane - 17;
                 if (c < (uint32_t)p.n_cols) { T->nb[c] = Sg->nb[c]; T->minv[c] = Sg->minv[c]; }
@@ -368,6 +371,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         // BK_RANK: this warp's buffer of out-of-range codes (the last ST_WARPS * ST_TBUF * 8 bytes of the group block)
         const uint32_t tbuf_saddr = smem_u32(gbase + p.group_bytes - (ST_WARPS - warp) * ST_TBUF * 8);
         uint32_t wtail = 0;
+        TCol c_kc = {0, 0, 0, 0, 0, 0}, c_bc[NBG ? NBG : 1], c_rc[NRG ? NRG : 1];
+        uint32_t c_seg = 0xffffffffu, c_base = 0, c_krel = 0;
+#pragma unroll
+        for (int g = 0; g < (NBG ? NBG : 1); g++) c_bc[g] = c_kc;
+#pragma unroll
+        for (int g = 0; g < (NRG ? NRG : 1); g++) c_rc[g] = c_kc;
         const uint32_t full_saddr = smem_u32(full), empty_saddr = smem_u32(empty);
         uint32_t stage = 0, parity = 0;
         for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
@@ -457,17 +466,33 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 }
             }
 
-            // per-tile column descriptors of the roles this instantiation has, in registers
+            // column descriptors of the roles this instantiation has, in registers; they depend on the segment only
+            // (bit width, min_value), so a tile of the same segment just moves the shared-memory address
             TCol kc, bc[NBG ? NBG : 1], rc[NRG ? NRG : 1];
             uint32_t krel = 0;  // TERMS: (column min - domain min); keys are dense and < 2^24 wide
-            if (BUCKET != BK_NONE) {
-                kc = tcol(p, T, stage_saddr, p.key_scol);
-                krel = (uint32_t)(lds64(T + TD_MINV(p.key_scol)) - p.dom_min);
+            const uint32_t tseg = lds32(T + TD_SEG);
+            if (tseg != c_seg) {
+                if (BUCKET != BK_NONE) {
+                    kc = tcol(p, T, stage_saddr, p.key_scol);
+                    krel = (uint32_t)(lds64(T + TD_MINV(p.key_scol)) - p.dom_min);
+                }
+#pragma unroll
+                for (int g = 0; g < NBG; g++) bc[g] = tcol(p, T, stage_saddr, p.bgroups[g].scol);
+#pragma unroll
+                for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
+                c_seg = tseg; c_base = stage_saddr; c_kc = kc; c_krel = krel;
+#pragma unroll
+                for (int g = 0; g < NBG; g++) c_bc[g] = bc[g];
+#pragma unroll
+                for (int g = 0; g < NRG; g++) c_rc[g] = rc[g];
+            } else {
+                const uint32_t moved = stage_saddr - c_base;
+                kc = c_kc; kc.saddr += moved; krel = c_krel;
+#pragma unroll
+                for (int g = 0; g < NBG; g++) { bc[g] = c_bc[g]; bc[g].saddr += moved; }
+#pragma unroll
+                for (int g = 0; g < NRG; g++) { rc[g] = c_rc[g]; rc[g].saddr += moved; }
             }
-#pragma unroll
-            for (int g = 0; g < NBG; g++) bc[g] = tcol(p, T, stage_saddr, p.bgroups[g].scol);
-#pragma unroll
-            for (int g = 0; g < NRG; g++) rc[g] = tcol(p, T, stage_saddr, p.rgroups[g].scol);
 
             // every f64 column this tile touches lies in [+0.0, +inf] (host-checked against the column headers):
             // code -> f64 is one XOR, and f64 min / max agree with the order of the codes
