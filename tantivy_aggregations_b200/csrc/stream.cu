@@ -1383,9 +1383,11 @@ static int stream_launch(ExecState& es, bool first_launch) {
         for (int g = 0; g < n_bgroups; g++) has_mm = has_mm || (sp.bgroups[g].ops & (OPB_MIN | OPB_MAX));
         size_t tb = lay_tables(false);
         // exact tables leave no room for a third consumer group but filter tables do: take the filter tables
-        if (has_mm && bucket_mode != BK_RANK && sp.dom_size <= (1u << 20) && tb + 3 * group_bytes(2) > SMEM_MAX) {
+        // (rank bins: always — a new extreme per bin is frequent enough that the 64-bit shared atomicMax, a CAS loop,
+        // shows up; the filter path is a 32-bit RED.MAX plus a global RED)
+        if (has_mm && sp.dom_size <= (1u << 20) && (bucket_mode == BK_RANK || tb + 3 * group_bytes(2) > SMEM_MAX)) {
             const size_t tf = lay_tables(true);
-            if (tf + 3 * group_bytes(2) <= SMEM_MAX) { sp.tab_filt = 1; tb = tf; }
+            if (tf + 3 * group_bytes(2) <= SMEM_MAX || bucket_mode == BK_RANK) { sp.tab_filt = 1; tb = tf; }
             else tb = lay_tables(false);
         }
         if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
