@@ -149,7 +149,6 @@ static int analyse(PlanMeta& m, uint32_t& pos, int parent, int scope, int depth)
         m.slot_of[me] = (int)m.slot_node.size();
         m.slot_node.push_back((int)me);
     } else if (d.op == TAGG_OP_PERCENTILES) {
-        if (scope != 0) return tagg_fail(TAGG_ERR_UNSUPPORTED, "node %u: percentiles nested under a bucket aggregation is not supported yet", me);
         if (m.pct_node.size() >= 4) return tagg_fail(TAGG_ERR_UNSUPPORTED, "more than 4 percentiles aggregations in a plan");
         m.pct_of[me] = (int)m.pct_node.size();
         m.pct_node.push_back((int)me);

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <unordered_map>
 #include <chrono>
 #include <stdio.h>
@@ -65,20 +66,92 @@ static int fetch(ExecState& es, const T* d_src, uint64_t capacity, const std::ve
 // Ranks kept from an exactly sorted multiset of n values: every rank up to 4096, then a geometric
 // schedule with ratio 1 + eps/4 (eps = 0.01, percentile.rs:174) so that any target rank k has a
 // stored rank within eps*k/8 — always inside CKMS's own +-eps*k band.
-static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks) {
+static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks, uint64_t dense_upto = 4096, double ratio = 0.0025) {
     ranks.clear();
-    uint64_t dense = std::min<uint64_t>(n, 4096);
+    uint64_t dense = std::min<uint64_t>(n, dense_upto);
     for (uint64_t r = 1; r <= dense; r++) ranks.push_back(r);
     uint64_t r = dense;
     while (r < n) {
-        uint64_t nx = r + std::max<uint64_t>(1, (uint64_t)((double)r * 0.0025));
+        uint64_t nx = r + std::max<uint64_t>(1, (uint64_t)((double)r * ratio));
         if (nx > n) nx = n;
         ranks.push_back(nx);
         r = nx;
     }
 }
 
-static int read_percentiles(ExecState& es, tagg_result* res) {
+// percentiles under a bucket aggregation: the materialised (code, bucket) pairs are sorted by code, then stably by
+// bucket; every run of one bucket is an exactly sorted multiset of which a rank schedule is kept (every rank up to 256,
+// then geometric with ratio 1 + eps/4 — the stored neighbour of any target rank is within eps/8 of it)
+static int read_nested_percentiles(ExecState& es, tagg_result* res, size_t k, uint64_t n, const std::vector<uint32_t>& raw_scope) {
+    uint64_t* d_codes_alt = nullptr;
+    uint32_t* d_bkt_alt = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_codes_alt, n * 8, es.st)); es.temps.push_back(d_codes_alt);
+    CUDA_TRY(cudaMallocAsync((void**)&d_bkt_alt, n * 4, es.st)); es.temps.push_back(d_bkt_alt);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64, es.st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n, 0, 32, es.st);
+    uint32_t *d_unique = nullptr, *d_counts = nullptr, *d_nruns = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_unique, n * 4, es.st)); es.temps.push_back(d_unique);
+    CUDA_TRY(cudaMallocAsync((void**)&d_counts, n * 4, es.st)); es.temps.push_back(d_counts);
+    CUDA_TRY(cudaMallocAsync((void**)&d_nruns, 16, es.st)); es.temps.push_back(d_nruns);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t3, (const uint32_t*)nullptr, d_unique, d_counts, d_nruns, (int)n, es.st);
+    void* d_tmp = nullptr;
+    const size_t tb = std::max(t1, std::max(t2, t3)) + 16;
+    CUDA_TRY(cudaMallocAsync(&d_tmp, tb, es.st)); es.temps.push_back(d_tmp);
+    size_t tt = tb;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tt, (const uint64_t*)es.pct_codes[k], d_codes_alt, (const uint32_t*)es.pct_buckets[k], d_bkt_alt, (int)n, 0, 64, es.st));
+    tt = tb;  // stable: codes stay ascending inside a bucket
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tt, (const uint32_t*)d_bkt_alt, es.pct_buckets[k], (const uint64_t*)d_codes_alt, es.pct_codes[k], (int)n, 0, 32, es.st));
+    tt = tb;
+    CUDA_TRY(cub::DeviceRunLengthEncode::Encode(d_tmp, tt, (const uint32_t*)es.pct_buckets[k], d_unique, d_counts, d_nruns, (int)n, es.st));
+    uint32_t nruns = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nruns, d_nruns, 4, cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    std::vector<uint32_t> uniq(nruns), counts(nruns);
+    CUDA_TRY(cudaMemcpyAsync(uniq.data(), d_unique, (size_t)nruns * 4, cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts, (size_t)nruns * 4, cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    // gather list: positions (1-based, into the grouped array) of the scheduled ranks of every run
+    std::vector<uint64_t> pos, rk;
+    std::vector<size_t> run_begin(nruns + 1, 0);
+    uint64_t off = 0;
+    for (uint32_t r = 0; r < nruns; r++) {
+        rank_schedule(counts[r], rk, 256, 0.0025);
+        run_begin[r] = pos.size();
+        for (uint64_t x : rk) pos.push_back(off + x);
+        off += counts[r];
+    }
+    run_begin[nruns] = pos.size();
+    std::vector<uint64_t> vals(pos.size());
+    if (!pos.empty()) {
+        uint64_t *d_pos = nullptr, *d_out = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&d_pos, pos.size() * 8, es.st)); es.temps.push_back(d_pos);
+        CUDA_TRY(cudaMallocAsync((void**)&d_out, pos.size() * 8, es.st)); es.temps.push_back(d_out);
+        CUDA_TRY(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, es.st));
+        k_gather_ranks<<<(unsigned)std::min<uint64_t>((pos.size() + 255) / 256, 4096), 256, 0, es.st>>>(es.pct_codes[k], d_pos, pos.size(), d_out);
+        es.ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(vals.data(), d_out, pos.size() * 8, cudaMemcpyDeviceToHost, es.st));
+        CUDA_TRY(cudaStreamSynchronize(es.st));
+    }
+    off = 0;
+    for (uint32_t r = 0; r < nruns; r++) {
+        PctSummary sum;
+        sum.n_total = counts[r];
+        for (size_t i = run_begin[r]; i < run_begin[r + 1]; i++) {
+            sum.ranks.push_back(pos[i] - off);
+            sum.value_bits.push_back(code_to_bits_h(TAGG_F64, vals[i]));
+        }
+        off += counts[r];
+        // raw bucket index of the enclosing scope -> compact bucket index of the result
+        auto it = std::lower_bound(raw_scope.begin(), raw_scope.end(), uniq[r]);
+        if (it == raw_scope.end() || *it != uniq[r]) return tagg_fail(TAGG_ERR_CUDA, "percentile values in a bucket that does not exist (internal error)");
+        res->pcts[k][(uint64_t)(it - raw_scope.begin())] = std::move(sum);
+    }
+    return 0;
+}
+
+static int read_percentiles(ExecState& es, tagg_result* res, const std::vector<std::vector<uint32_t>>& raw) {
     const PlanMeta& m = *es.meta;
     res->pcts.resize(m.pct_node.size());
     for (size_t k = 0; k < m.pct_node.size(); k++) {
@@ -95,6 +168,13 @@ static int read_percentiles(ExecState& es, tagg_result* res) {
         CUDA_TRY(cudaMemcpyAsync(&n, es.pct_count[k], 8, cudaMemcpyDeviceToHost, es.st));
         CUDA_TRY(cudaStreamSynchronize(es.st));
         if (n > es.pct_cap[k]) n = es.pct_cap[k];
+        if (m.scope_of[m.pct_node[k]] != 0) {  // under a bucket aggregation
+            if (n) {
+                int rc = read_nested_percentiles(es, res, k, n, raw[m.scope_of[m.pct_node[k]]]);
+                if (rc) return rc;
+            }
+            continue;
+        }
         sum.n_total = n;
         if (n) {
             uint64_t* d_alt = nullptr;
@@ -252,7 +332,7 @@ int read_result(ExecState& es, tagg_result* res) {
         }
     }
     lap("slots");
-    return read_percentiles(es, res);
+    return read_percentiles(es, res, raw);
 }
 
 // ---- PreparedAgg::merge on compact results --------------------------------------------------------
@@ -363,7 +443,8 @@ int result_merge(tagg_result* dst, const tagg_result* src) {
         }
     }
     for (size_t k = 0; k < m.pct_node.size(); k++) {
-        for (auto& kv : src->pcts[k]) merge_pct(dst->pcts[k][kv.first], kv.second);
+        const int sc = m.scope_of[m.pct_node[k]];
+        for (auto& kv : src->pcts[k]) merge_pct(dst->pcts[k][sc == 0 ? kv.first : (uint64_t)map[sc][kv.first]], kv.second);
     }
     dst->kernel_ms += src->kernel_ms;
     dst->alg_bytes += src->alg_bytes;
