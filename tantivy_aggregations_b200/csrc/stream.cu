@@ -81,11 +81,15 @@ struct SParams {
     uint32_t soff_tab_count[2];                    // STAB: CTA-private bucket count tables (u32)
     uint32_t soff_tab_sum[ST_MAXBG];               // STAB: CTA-private bucket sum tables (u64 / f64)
     uint32_t soff_tab_min[ST_MAXBG], soff_tab_max[ST_MAXBG];  // STAB: CTA-private min / max tables (u64, max-form)
-    // STAB with filter tables: the shared min / max tables hold only the HIGH 32 bits of the CTA's best value (u32) and
+    // STAB with filter tables: the shared min / max tables hold only a 32-bit rank word of the CTA's best value (u32) and
     // act as a filter in front of the exact global cells (a value whose high word does not reach the filter cannot be a
     // new extreme); survivors — a few per bucket and CTA — go to the global table with a checked atomic.  Halves the
     // table footprint so that a third consumer group fits (C2: 0.253 -> 0.21 ms)
+    // The filter word is the value's position inside the column's code range [filt_lo, filt_hi] over all segments of the
+    // call, scaled to 32 bits: (code - lo) >> shift for max, (hi - code) >> shift for min (so integer columns filter too)
     uint32_t tab_filt;
+    uint32_t filt_shift[ST_MAXBG];
+    uint64_t filt_lo[ST_MAXBG], filt_hi[ST_MAXBG];
     int32_t n_preds, n_vpreds;                     // all predicates / those evaluated on column values
     int32_t pred_type[ST_MAXPRED];
     int32_t pred_scol[ST_MAXPRED];
@@ -536,7 +540,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 constexpr int U = decltype(U_)::value;
                 constexpr bool CHECK = decltype(CHECK_)::value;
                 constexpr bool POS = decltype(POS_)::value;
-                auto c2f = [](uint64_t code) { return POS ? __longlong_as_double((long long)(code ^ 0x8000000000000000ull)) : code_to_f64(code); };
+                // (BK_RANK keeps ONE instantiation and branches on the per-tile flag: its code already crowds the instruction cache)
+                auto c2f = [&](uint64_t code) {
+                    if (BUCKET == BK_RANK) return fpos ? __longlong_as_double((long long)(code ^ 0x8000000000000000ull)) : code_to_f64(code);
+                    return POS ? __longlong_as_double((long long)(code ^ 0x8000000000000000ull)) : code_to_f64(code);
+                };
                 // histogram ordinal of a code relative to the first bucket, -1: skipped (NaN or below start, histogram.rs:138-145).
                 // A multiply lands next to the exact ordinal; the boundary table (exact, monotone in the code) decides.
                 auto hist_bin = [&](uint64_t code) -> int {
@@ -682,9 +690,9 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(nfb[u]) : "r"(smem_saddr + p.soff_nib + rel[u]));
                                     const uint64_t lv = code[u] >= p.nib_lo ? (code[u] - p.nib_lo) >> p.nib_shift : 0ull;
                                     nq[u] = lv > 15 ? 15u : (uint32_t)lv;
-                                } else if (filt) {
-                                    if (ops & OPB_MIN) cur_min[u] = (uint64_t)lds32(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]) << 32;
-                                    if (ops & OPB_MAX) cur_max[u] = (uint64_t)lds32(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]) << 32;
+                                } else if (filt) {  // cur_* hold the filter word; code[u] is compared through its own rank word below
+                                    if (ops & OPB_MIN) cur_min[u] = lds32(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]);
+                                    if (ops & OPB_MAX) cur_max[u] = lds32(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]);
                                 } else {
                                     if (ops & OPB_MIN) cur_min[u] = STAB ? lds64(smem_saddr + p.soff_tab_min[g] + 8 * rel[u]) : G.acc_min[rel[u]];
                                     if (ops & OPB_MAX) cur_max[u] = STAB ? lds64(smem_saddr + p.soff_tab_max[g] + 8 * rel[u]) : G.acc_max[rel[u]];
@@ -707,18 +715,29 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                     if (nx != fx || nn != fn) asm volatile("st.shared.u8 [%0], %1;" ::"r"(smem_saddr + p.soff_nib + rel[u]), "r"((nx << 4) | nn) : "memory");
                                     continue;
                                 }
+                                if (filt) {  // fire-and-forget: no load sits between the filter and the global RED
+                                    if (ops & OPB_MIN) {
+                                        const uint32_t q = (uint32_t)((p.filt_hi[g] - code[u]) >> p.filt_shift[g]);
+                                        if (q >= (uint32_t)cur_min[u]) {
+                                            if (q > (uint32_t)cur_min[u]) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]), "r"(q) : "memory");
+                                            atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
+                                        }
+                                    }
+                                    if (ops & OPB_MAX) {
+                                        const uint32_t q = (uint32_t)((code[u] - p.filt_lo[g]) >> p.filt_shift[g]);
+                                        if (q >= (uint32_t)cur_max[u]) {
+                                            if (q > (uint32_t)cur_max[u]) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]), "r"(q) : "memory");
+                                            atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
+                                        }
+                                    }
+                                    continue;
+                                }
                                 if ((ops & OPB_MIN) && cur_min[u] < ~code[u]) {
-                                    if (filt) {  // fire-and-forget: no load sits between the filter and the global RED
-                                        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]), "r"((uint32_t)(~code[u] >> 32)) : "memory");
-                                        atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
-                                    } else if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_min[g]) + rel[u], (unsigned long long)~code[u]);
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_min[g]) + rel[u], (unsigned long long)~code[u]);
                                     else if (__ldcg(G.acc_min + rel[u]) < ~code[u]) atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
                                 }
                                 if ((ops & OPB_MAX) && cur_max[u] < code[u]) {
-                                    if (filt) {
-                                        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]), "r"((uint32_t)(code[u] >> 32)) : "memory");
-                                        atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
-                                    } else if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_max[g]) + rel[u], (unsigned long long)code[u]);
+                                    if (STAB) atomicMax((unsigned long long*)(smem + p.soff_tab_max[g]) + rel[u], (unsigned long long)code[u]);
                                     else if (__ldcg(G.acc_max + rel[u]) < code[u]) atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
                                 }
                             }
@@ -727,7 +746,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 }
             };
             // the non-negative fast path is instantiated where it pays: CT shapes and histograms
-            constexpr bool HAS_POS = SH::BOPS >= 0 || SH::ROPS >= 0 || BUCKET == BK_HIST || BUCKET == BK_RANK;
+            constexpr bool HAS_POS = (SH::BOPS >= 0 || SH::ROPS >= 0 || BUCKET == BK_HIST) && BUCKET != BK_RANK;
             auto run = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
                 if (HAS_POS && fpos) process(U_, CHECK_, std::true_type{}, dl, act_in);
                 else process(U_, CHECK_, std::false_type{}, dl, act_in);
@@ -771,13 +790,18 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     dl[0] = d0; dl[1] = d1;
                     run(I2{}, std::true_type{}, dl, act);
                 } else if (j0 < nq) {
-                    uint32_t dl[1];
-                    bool act[1];
-                    act[0] = j0 + lane < nq;
                     uint16_t d0 = 0;
-                    if (act[0]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
-                    dl[0] = d0;
-                    run(I1{}, std::true_type{}, dl, act);
+                    const bool a0 = j0 + lane < nq;
+                    if (a0) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(d0) : "r"(q_saddr + 2 * (j0 + lane)));
+                    if (BUCKET == BK_RANK) {  // one ragged instantiation only (instruction-cache footprint)
+                        uint32_t dl[2] = {d0, 0};
+                        bool act[2] = {a0, false};
+                        run(I2{}, std::true_type{}, dl, act);
+                    } else {
+                        uint32_t dl[1] = {d0};
+                        bool act[1] = {a0};
+                        run(I1{}, std::true_type{}, dl, act);
+                    }
                 }
             } else {
                 // nothing narrows the doc stream: every document of the tile is matched (ragged only in a
@@ -1392,6 +1416,23 @@ static int stream_launch(ExecState& es, bool first_launch) {
         }
         if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
         else sp.tab_filt = 0;
+        if (sp.tab_filt) {
+            for (int g = 0; g < n_bgroups; g++) {
+                uint64_t glo = ~0ull, ghi = 0;
+                for (auto& hs : es.hsegs) {
+                    const DevColumn& col = hs.cols[sh.staged[sp.bgroups[g].scol]];
+                    if (!col.n_values) continue;
+                    glo = std::min(glo, col.min_value);
+                    ghi = std::max(ghi, col.max_value);
+                }
+                if (glo > ghi) { glo = 0; ghi = 0; }
+                const uint64_t span = ghi - glo;
+                const uint32_t bits = span ? 64 - (uint32_t)__builtin_clzll(span) : 0;
+                sp.filt_lo[g] = glo;
+                sp.filt_hi[g] = ghi;
+                sp.filt_shift[g] = bits > 32 ? bits - 32 : 0;
+            }
+        }
     }
     // histogram with few buckets (the launch's bucket node, or the one fused into a percentile pass): exact code
     // boundaries of the ordinals

@@ -213,3 +213,37 @@ def test_cached_device_docsets(ctx, world):
     want, _, _ = ox.search(ta.AllQuery(), agg(host_q))
     assert_fruit_equal(searcher.agg_search(ta.AllQuery(), agg(cached)), want)
     assert_fruit_equal(searcher.agg_search(cached, ta.count_agg()), ox.search(host_q, ta.count_agg())[0])
+
+
+def test_filter_tables_and_level_filters_on_integer_columns(ctx):
+    """Bucket min / max behind the shared-memory filters (u32 rank words when the exact tables would crowd out a consumer
+    group, 4-bit levels when the tables live in global memory) on integer and date columns, several segments with different
+    column ranges."""
+    rng = np.random.default_rng(17)
+    segs = []
+    for i, n in enumerate((150_000, 90_001, 4096)):
+        s = SegSpec(n)
+        s.col(CAT, F.U64, rng.integers(1, 12_001, size=n, dtype=np.uint64))
+        s.col(WIDE, F.U64, rng.integers(1, 200_001, size=n, dtype=np.uint64))
+        s.col(STATUS, F.U64, rng.integers(0, 1000 * (i + 1), size=n, dtype=np.uint64))
+        s.col(SIGNED, F.I64, rng.integers(-10_000 * (i + 1), 10_000, size=n, dtype=np.int64))
+        s.col(WHEN, F.DATE, rng.integers(1_500_000_000, 1_500_000_000 + 10**6 * (i + 1), size=n, dtype=np.int64))
+        s.col(PRICE, F.F64, rng.normal(0.0, 100.0, size=n))
+        s.deleted = rng.choice(n, size=n // 20, replace=False)
+        segs.append(s)
+    corpus = Corpus(segs)
+    searcher, ox = corpus.build_gpu(ctx), corpus.build_oracle()
+    shapes = {
+        "u32_filter": lambda: ta.terms_agg_u64(CAT, (ta.count_agg(), ta.min_agg_u64(STATUS), ta.max_agg_u64(STATUS), ta.min_agg_i64(SIGNED), ta.max_agg_date(WHEN))),
+        "u32_filter_f64_signed": lambda: ta.terms_agg_u64(CAT, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_i64(SIGNED))),
+        "level_filter": lambda: ta.terms_agg_u64(WIDE, (ta.min_agg_i64(SIGNED), ta.max_agg_i64(SIGNED), ta.sum_agg_i64(SIGNED))),
+        "level_filter_f64": lambda: ta.post_filter_agg_u64(STATUS, ta.lt(500), ta.terms_agg_u64(WIDE, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE)))),
+    }
+    for name, mk in shapes.items():
+        want, _, _ = ox.search(ta.AllQuery(), mk())
+        ctx.set_path(F.PATH_STREAM)
+        try:
+            got = searcher.agg_search(ta.AllQuery(), mk())
+        finally:
+            ctx.set_path(F.PATH_AUTO)
+        assert_fruit_equal(got, want, F64_SUM_RTOL, name)
