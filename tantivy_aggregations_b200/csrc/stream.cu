@@ -807,7 +807,37 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 // nothing narrows the doc stream: every document of the tile is matched (ragged only in a
                 // segment's last tile)
                 const uint32_t wbase = warp * ST_DOCS_PER_WARP;
-                if (n_valid == ST_TILE) {
+                if (CTROOT && n_valid == ST_TILE) {
+                    // The lane's 8 values sit 32 values = nb words apart: one address, one shift amount and one mask pair
+                    // serve all of them (the generic unpack recomputes them per value).  Width and sign class are uniform
+                    // over the tile, so the loop is instantiated for each instead of predicated.
+                    matched += ST_DOCS_PER_WARP;
+                    rseen = true;
+                    fseen = true;
+                    const TCol& c = rc[0];
+                    const uint32_t bit0 = (wbase + lane) * c.nb, sh = bit0 & 31u, stepb = c.nb * 4;
+                    const uint32_t a0 = c.saddr + ((bit0 >> 5) << 2);
+                    auto dense = [&](auto WIDE_, auto POS_) {
+                        constexpr bool WIDE = decltype(WIDE_)::value, POS = decltype(POS_)::value;
+                        uint32_t a = a0;
+#pragma unroll
+                        for (int k = 0; k < ST_WORDS_PER_WARP; k++, a += stepb) {
+                            const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+                            const uint32_t lo = __funnelshift_r(w0, w1, sh) & c.mlo;
+                            uint32_t hi = 0;
+                            if (WIDE) hi = __funnelshift_r(w1, lds32(a + 8), sh) & c.mhi;
+                            const uint64_t d = ((uint64_t)hi << 32) | lo;
+                            if (SH::ROPS & OPB_SUM) {
+                                const double v = POS ? __longlong_as_double((long long)(d + rbase)) : code_to_f64(d + cminv);
+                                rsum[0] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rsum[0]), v));
+                            }
+                            if (SH::ROPS & OPB_MIN) dmin = d < dmin ? d : dmin;
+                            if (SH::ROPS & OPB_MAX) dmax = d > dmax ? d : dmax;
+                        }
+                    };
+                    if (c.nb > 32) { if (fpos) dense(std::true_type{}, std::true_type{}); else dense(std::true_type{}, std::false_type{}); }
+                    else { if (fpos) dense(std::false_type{}, std::true_type{}); else dense(std::false_type{}, std::false_type{}); }
+                } else if (n_valid == ST_TILE) {
                     matched += ST_DOCS_PER_WARP;
 #pragma unroll
                     for (int j0 = 0; j0 < ST_WORDS_PER_WARP; j0 += 4) {
