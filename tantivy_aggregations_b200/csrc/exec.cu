@@ -163,7 +163,7 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
             h2d += bytes(inputs[i].docset);
             for (uint32_t f = 0; f < m.n_filters && f < inputs[i].n_filters; f++) h2d += bytes(inputs[i].filters[f]);
         }
-        es.n_chunks = (h2d >= (1u << 20) && n_inputs >= 2) ? std::min<uint32_t>(4, n_inputs) : 1;
+        { static const char* ov = getenv("TAGG_CHUNKS"); const uint32_t maxc = ov ? (uint32_t)atoi(ov) : 4u; es.n_chunks = (h2d >= (1u << 20) && n_inputs >= 2) ? std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(maxc, 1u), 8u), n_inputs) : 1; }
         es.chunk_begin.assign(es.n_chunks + 1, 0);
         for (uint32_t c = 0; c <= es.n_chunks; c++) es.chunk_begin[c] = (uint32_t)((uint64_t)n_inputs * c / es.n_chunks);
     }

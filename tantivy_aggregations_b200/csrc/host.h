@@ -31,7 +31,7 @@ struct CallRes {
     cudaStream_t st = nullptr;   // uploads, downloads, ordering
     cudaStream_t st2 = nullptr;  // upload stream: host docsets cross PCIe here while kernels of earlier chunks run on st
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev = nullptr;
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, join_ev = nullptr;
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0, pinned_used = 0;
 };
