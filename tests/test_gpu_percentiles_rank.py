@@ -66,6 +66,11 @@ def test_rank_bin_percentiles(ctx, name):
     (cnt, hist, p2) = searcher.agg_search(ta.AllQuery(), (ta.count_agg(), ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)))
     assert cnt == N
     check(p2, vals)
+    if name in ("uniform_price", "lognormal", "narrow_normal", "discrete_ties", "normal_signed"):
+        # the histogram (fused into the percentile pass where both stream) against numpy: histogram.rs:136-152
+        ok = vals - 0.0 >= 0.0
+        ords, counts = np.unique(np.floor(vals[ok] / 10.0).astype(np.int64), return_counts=True)
+        assert dict(hist._buckets) == {int(o): int(c) for o, c in zip(ords, counts)}
 
 
 def test_rank_bin_percentiles_under_filters(ctx):
