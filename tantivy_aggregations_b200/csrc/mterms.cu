@@ -27,11 +27,12 @@
 #define MT_SUB_THREADS 256
 #define MT_MAXSUB 3
 #define MT_TILE 1024     // documents per sub-block tile
+#define MT_TILE_BITS 10
 #define MT_CHUNK 8192    // key occurrences expanded at a time
 #define MT_MAXGROUPS 2
 #define MT_MAXPRED NARROW_MAXPRED
 #define MT_MAXCOUNTS 2
-#define MT_U 4           // key occurrences in flight per thread
+#define MT_U 4           // key occurrences in flight per thread (8 spills)
 #define MT_DU (MT_TILE / MT_SUB_THREADS)  // documents per thread in the doc phase
 
 enum { MO_SUM = 1, MO_MIN = 2, MO_MAX = 4 };
@@ -241,11 +242,18 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
         for (uint32_t cbase = 0; cbase < nk; cbase += MT_CHUNK) {
             const uint32_t cn = min((uint32_t)MT_CHUNK, nk - cbase);
             // ---- expand: tile-local document index of every key occurrence of the chunk ------------------
+            // (the document's flag bits ride in the top bits of the entry: one shared load per occurrence)
             for (uint32_t i = st; i < nd; i += MT_SUB_THREADS) {
                 uint32_t lo = max(koff[i], cbase), hi = min(koff[i + 1], cbase + cn);
-                for (uint32_t v = lo; v < hi; v++) docof[v - cbase] = (uint16_t)i;
+                const uint16_t e = (uint16_t)(i | ((uint32_t)flags[i] << MT_TILE_BITS));
+                for (uint32_t v = lo; v < hi; v++) docof[v - cbase] = e;
             }
             named_bar(1 + sub, MT_SUB_THREADS);
+            const uint32_t knb = cs[1].nb, kmask = (uint32_t)cs[1].mask;
+            const bool k32 = knb >= 1 && knb <= 32;
+            const uint64_t kminv = cs[1].minv, kbit0 = (kbase + cbase) * knb;
+            const uint32_t* kwp = (const uint32_t*)cs[1].words + (kbit0 >> 5);
+            const uint32_t ksh0 = (uint32_t)kbit0 & 31u;
             // ---- value phase: one thread per key occurrence (terms.rs:172-179), MT_U occurrences in flight ---
             for (uint32_t v0 = st; v0 < cn; v0 += MT_SUB_THREADS * MT_U) {
                 uint32_t di[MT_U], f[MT_U], b[MT_U];
@@ -253,9 +261,16 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
 #pragma unroll
                 for (int u = 0; u < MT_U; u++) {
                     const uint32_t v = min(v0 + u * MT_SUB_THREADS, cn - 1);
-                    di[u] = docof[v];
-                    f[u] = v0 + u * MT_SUB_THREADS < cn ? flags[di[u]] : 0u;
-                    key[u] = cget(cs[1], kbase + cbase + v);
+                    const uint32_t e = docof[v];
+                    di[u] = e & (MT_TILE - 1);
+                    f[u] = v0 + u * MT_SUB_THREADS < cn ? e >> MT_TILE_BITS : 0u;
+                    if (k32) {  // narrow keys: 32-bit arithmetic relative to the chunk's first key
+                        const uint32_t bb = ksh0 + v * knb;
+                        const uint32_t* w = kwp + (bb >> 5);
+                        key[u] = (uint64_t)(__funnelshift_r(__ldg(w), __ldg(w + 1), bb & 31u) & kmask) + kminv;
+                    } else {
+                        key[u] = cget(cs[1], kbase + cbase + v);
+                    }
                 }
                 if (DENSE) {
 #pragma unroll
@@ -286,7 +301,8 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
 #pragma unroll
                         for (int u = 0; u < MT_U; u++)
                             if (((f[u] >> (1 + g)) & 1u) && !G.seen[b[u]]) G.seen[b[u]] = 1;
-                    } else if (G.seen_mode == SEEN_DERIVED) {  // a contribution equal to the identity leaves no trace in the cell
+                    } else if (G.seen_mode == SEEN_DERIVED && G.derive_op != MO_SUM) {  // a contribution equal to the identity leaves
+                        // no trace in the cell (a folded f64 sum starts from +0.0 and is never the -0.0 identity)
                         const uint64_t* ss = (const uint64_t*)(base + (G.derive_op == MO_SUM ? G.soff_sum : G.derive_op == MO_MIN ? G.soff_min : G.soff_max));
                         const uint64_t ident = G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull;
 #pragma unroll
