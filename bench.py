@@ -225,10 +225,14 @@ def run_b200(args):
 
     # the filter query's matched docs: on the host as pinned bitsets (what decoding the postings of
     # `status=0` yields; here evaluated once from the fast field) and cached on the device
+    # (slices of ONE pinned buffer: equal-sized segments then cross PCIe as one 2-D copy per chunk)
     host_bits = {}
-    for seg in segments:
+    need = (per_seg + 7) // 8
+    pinned_all = torch.empty(need * len(segments), dtype=torch.uint8).pin_memory()
+    for i, seg in enumerate(segments):
         b = seg.docset_to_bitset(status_q.docset(seg))
-        pinned = torch.empty(len(b), dtype=torch.uint8).pin_memory()
+        assert len(b) == need
+        pinned = pinned_all[i * need:(i + 1) * need]
         pinned.numpy()[:] = b
         host_bits[seg.ord] = pinned
     host_filter = ta.BitsetQuery({k: v.numpy() for k, v in host_bits.items()})

@@ -63,7 +63,7 @@ static int dev_alloc(ExecState& es, T** out, size_t bytes) {
 }
 
 // A docset argument -> what the kernels test (dev.cuh DevDocset).
-static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg_index, const tagg_docset& in, bool is_main,
+static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg_index, const tagg_docset& in, bool is_main, int slot,
                             DevSegment& hs, int& next_col, DevDocset* out, uint64_t* n_cand) {
     DevDocset d;
     memset(&d, 0, sizeof(d));
@@ -79,10 +79,17 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg
                 return tagg_fail(TAGG_ERR_BAD_ARG, "bitset docset needs %zu bytes for max_doc=%u, got %llu", need, seg->max_doc,
                                  (unsigned long long)in.n);
             uint32_t* w = nullptr;
-            int rc = dev_alloc(es, &w, words * 4);
-            if (rc) return rc;
-            { size_t tail = need / 4; CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st)); }
-            if (need) es.uploads.push_back({w, in.data, need, seg_index, nullptr, 0});
+            const size_t take = (words * 4 + 255) & ~(size_t)255;
+            if (es.ds_block && es.ds_used + take <= es.ds_bytes) {  // sub-allocated from the call's zeroed docset block
+                w = (uint32_t*)(es.ds_block + es.ds_used);
+                es.ds_used += take;
+            } else {
+                int rc = dev_alloc(es, &w, words * 4);
+                if (rc) return rc;
+                size_t tail = need / 4;
+                CUDA_TRY(cudaMemsetAsync(w + tail, 0, (words - tail) * 4, es.st));
+            }
+            if (need) es.uploads.push_back({w, in.data, need, seg_index, nullptr, 0, slot});
             d.kind = DS_BITSET;
             d.words = w;
             if (n_cand) *n_cand = seg->max_doc;
@@ -110,7 +117,7 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg
                 if (rc) return rc;
                 CUDA_TRY(cudaMemsetAsync(scatter, 0, words * 4, es.st));
             }
-            if (in.n) es.uploads.push_back({ids, in.data, (size_t)in.n * 4, seg_index, scatter, in.n});
+            if (in.n) es.uploads.push_back({ids, in.data, (size_t)in.n * 4, seg_index, scatter, in.n, slot});
             es.alg_bytes += in.n * 4;
             if (is_main) {
                 d.kind = DS_IDS;
@@ -163,7 +170,50 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
             h2d += bytes(inputs[i].docset);
             for (uint32_t f = 0; f < m.n_filters && f < inputs[i].n_filters; f++) h2d += bytes(inputs[i].filters[f]);
         }
-        { static const char* ov = getenv("TAGG_CHUNKS"); const uint32_t maxc = ov ? (uint32_t)atoi(ov) : 4u; es.n_chunks = (h2d >= (1u << 20) && n_inputs >= 2) ? std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(maxc, 1u), 8u), n_inputs) : 1; }
+        // Bitsets that are slices of one host buffer (constant stride, equal segments) travel as ONE 2-D copy: on this
+        // platform a PCIe copy has a ~60-90 us floor, so one big copy followed by one launch beats any chunking
+        // (measured, C2 e2e: 1 chunk 0.63 ms, 2: 0.67, 4: 0.74, 8: 0.86)
+        bool one_copy = n_inputs >= 2 && h2d >= (1u << 20);
+        ptrdiff_t strides[1 + TAGG_MAX_FILTERS] = {0};
+        for (uint32_t i = 0; one_copy && i + 1 < n_inputs; i++) {
+            const tagg_segment_input &a = inputs[i], &b = inputs[i + 1];
+            if (!a.segment || !b.segment || a.segment->max_doc != b.segment->max_doc) { one_copy = false; break; }
+            auto strided = [&](const tagg_docset& x, const tagg_docset& y, ptrdiff_t* stride) {
+                if (x.kind != y.kind) return false;
+                if (x.kind == TAGG_DOCSET_SORTED_IDS) return false;
+                if (x.kind != TAGG_DOCSET_BITSET) return true;
+                const ptrdiff_t d = (const uint8_t*)y.data - (const uint8_t*)x.data;
+                if (d < (ptrdiff_t)(((size_t)a.segment->max_doc + 7) / 8)) return false;
+                if (*stride && *stride != d) return false;
+                *stride = d;
+                return true;
+            };
+            if (!strided(a.docset, b.docset, &strides[0])) one_copy = false;
+            for (uint32_t f = 0; one_copy && f < m.n_filters && f < a.n_filters && f < b.n_filters; f++)
+                if (!strided(a.filters[f], b.filters[f], &strides[1 + f])) one_copy = false;
+        }
+        if (one_copy) { es.n_chunks = 1; }
+        else { static const char* ov = getenv("TAGG_CHUNKS"); const uint32_t maxc = ov ? (uint32_t)atoi(ov) : 4u; es.n_chunks = (h2d >= (1u << 20) && n_inputs >= 2) ? std::min<uint32_t>(std::min<uint32_t>(std::max<uint32_t>(maxc, 1u), 8u), n_inputs) : 1; }
+        {   // one zeroed device block for every host bitset docset of the call
+            size_t total = 0;
+            auto words_of = [](const tagg_segment* sg) { return (((size_t)sg->max_doc + TAGG_TILE_DOCS - 1) / TAGG_TILE_DOCS) * (TAGG_TILE_DOCS / 32) + 16; };
+            for (uint32_t i = 0; i < n_inputs; i++) {
+                if (!inputs[i].segment) continue;
+                const size_t take = (words_of(inputs[i].segment) * 4 + 255) & ~(size_t)255;
+                if (inputs[i].docset.kind == TAGG_DOCSET_BITSET) total += take;
+                for (uint32_t f = 0; f < m.n_filters && f < inputs[i].n_filters; f++)
+                    if (inputs[i].filters[f].kind == TAGG_DOCSET_BITSET) total += take;
+            }
+            if (total) {
+                void* blk = nullptr;
+                CUDA_TRY(cudaMallocAsync(&blk, total, es.st));
+                es.temps.push_back(blk);
+                CUDA_TRY(cudaMemsetAsync(blk, 0, total, es.st));
+                es.ds_block = (uint8_t*)blk;
+                es.ds_bytes = total;
+                es.ds_used = 0;
+            }
+        }
         es.chunk_begin.assign(es.n_chunks + 1, 0);
         for (uint32_t c = 0; c <= es.n_chunks; c++) es.chunk_begin[c] = (uint32_t)((uint64_t)n_inputs * c / es.n_chunks);
     }
@@ -199,10 +249,10 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
             }
         }
         int next_col = at;
-        int rc = normalise_docset(es, seg, i, inputs[i].docset, true, hs, next_col, &hs.main, &es.n_cand[i]);
+        int rc = normalise_docset(es, seg, i, inputs[i].docset, true, 0, hs, next_col, &hs.main, &es.n_cand[i]);
         if (rc) return rc;
         for (uint32_t f = 0; f < m.n_filters; f++) {
-            rc = normalise_docset(es, seg, i, inputs[i].filters[f], false, hs, next_col, &hs.filters[f], nullptr);
+            rc = normalise_docset(es, seg, i, inputs[i].filters[f], false, 1 + (int)f, hs, next_col, &hs.filters[f], nullptr);
             if (rc) return rc;
         }
     }
@@ -217,8 +267,34 @@ static int issue_uploads(ExecState& es) {
     CUDA_TRY(cudaStreamWaitEvent(up, es.call->join_ev, 0));
     size_t at = 0;
     for (uint32_t c = 0; c < es.n_chunks; c++) {
-        for (; at < es.uploads.size() && es.uploads[at].seg < es.chunk_begin[c + 1]; at++) {
-            auto& u = es.uploads[at];
+        const size_t c0 = at;
+        while (at < es.uploads.size() && es.uploads[at].seg < es.chunk_begin[c + 1]) at++;
+        std::vector<uint8_t> done(at - c0, 0);
+        // same-slot bitsets of consecutive segments at constant source and destination strides: one 2-D copy
+        for (size_t i = c0; i < at; i++) {
+            if (done[i - c0] || es.uploads[i].scatter_words) continue;
+            std::vector<size_t> run = {i};
+            for (size_t j = i + 1; j < at; j++) {
+                const auto &a = es.uploads[run.back()], &b = es.uploads[j];
+                if (done[j - c0] || b.scatter_words || b.slot != a.slot || b.bytes != a.bytes || b.seg != a.seg + 1) continue;
+                const ptrdiff_t ss = (const uint8_t*)b.src - (const uint8_t*)a.src, ds = (uint8_t*)b.dst - (uint8_t*)a.dst;
+                if (ss < (ptrdiff_t)a.bytes || ds < (ptrdiff_t)a.bytes) break;
+                if (run.size() >= 2) {
+                    const auto& z = es.uploads[run[run.size() - 2]];
+                    if (ss != (const uint8_t*)a.src - (const uint8_t*)z.src || ds != (uint8_t*)a.dst - (uint8_t*)z.dst) break;
+                }
+                run.push_back(j);
+            }
+            if (run.size() >= 2) {
+                const auto &a = es.uploads[run[0]], &b = es.uploads[run[1]];
+                CUDA_TRY(cudaMemcpy2DAsync(a.dst, (size_t)((uint8_t*)b.dst - (uint8_t*)a.dst), a.src, (size_t)((const uint8_t*)b.src - (const uint8_t*)a.src),
+                                           a.bytes, run.size(), cudaMemcpyHostToDevice, up));
+                for (size_t k : run) done[k - c0] = 1;
+            }
+        }
+        for (size_t i = c0; i < at; i++) {
+            if (done[i - c0]) continue;
+            auto& u = es.uploads[i];
             CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, up));
             if (u.scatter_words) {
                 CUDA_TRY(launch_ids_to_bitset((const uint32_t*)u.dst, u.scatter_n, u.scatter_words, up));

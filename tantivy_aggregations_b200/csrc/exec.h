@@ -95,7 +95,12 @@ struct ExecState {
     uint32_t path_used = 0;
     // chunked execute: host docsets are uploaded on a second stream, segments grouped into chunks; the kernels of
     // chunk c wait only for chunk c's uploads (chunk_ev[c]) while later chunks are still crossing PCIe
-    struct PendingUpload { void* dst; const void* src; size_t bytes; uint32_t seg; uint32_t* scatter_words; uint64_t scatter_n; };
+    struct PendingUpload { void* dst; const void* src; size_t bytes; uint32_t seg; uint32_t* scatter_words; uint64_t scatter_n; int slot; };
+    // all host bitset docsets of a call live in ONE device block (zeroed once): segments of equal size then sit at a
+    // constant stride, and if the caller's buffers do too (slices of one pinned buffer) a chunk crosses PCIe as a single
+    // 2-D copy instead of one small copy per segment
+    uint8_t* ds_block = nullptr;
+    size_t ds_bytes = 0, ds_used = 0;
     std::vector<PendingUpload> uploads;  // host docsets: issued on call->st2 (the upload stream) after the allocations
     uint32_t n_chunks = 1;
     std::vector<uint32_t> chunk_begin;  // n_chunks + 1 segment indices
