@@ -78,6 +78,24 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg
             if (need && (!in.data || in.n < need))
                 return tagg_fail(TAGG_ERR_BAD_ARG, "bitset docset needs %zu bytes for max_doc=%u, got %llu", need, seg->max_doc,
                                  (unsigned long long)in.n);
+            {   // a page-locked, device-mapped host buffer (cudaHostAlloc / cudaHostRegister) is read IN PLACE: the streaming
+                // kernel's TMA producer pulls each 256-byte tile over PCIe exactly once, overlapped with the column tiles —
+                // no staging copy, no copy-engine latency.  Needs 16-byte alignment and room for whole 16-byte reads.
+                static const bool no_direct = getenv("TAGG_NO_DIRECT") != nullptr;
+                const size_t need16 = (need + 15) & ~(size_t)15;
+                cudaPointerAttributes attr;
+                if (!no_direct && need && in.n >= need16 && cudaPointerGetAttributes(&attr, in.data) == cudaSuccess &&
+                    attr.type == cudaMemoryTypeHost && attr.devicePointer && ((uintptr_t)attr.devicePointer & 15) == 0) {
+                    d.kind = DS_BITSET;
+                    d.words = (const uint32_t*)attr.devicePointer;
+                    d.n = need16;
+                    if (n_cand) *n_cand = seg->max_doc;
+                    es.alg_bytes += need;
+                    es.direct_bytes += need;
+                    break;
+                }
+                cudaGetLastError();
+            }
             uint32_t* w = nullptr;
             const size_t take = (words * 4 + 255) & ~(size_t)255;
             if (es.ds_block && es.ds_used + take <= es.ds_bytes) {  // sub-allocated from the call's zeroed docset block

@@ -91,6 +91,7 @@ struct ExecState {
     bool no_rank = false;            // a rank-bin pass failed its precision check: redo on the exact path
 
     uint64_t alg_bytes = 0;
+    uint64_t direct_bytes = 0;  // host docset bytes the kernels read in place over PCIe
     uint32_t n_launches = 0;
     uint32_t path_used = 0;
     // chunked execute: host docsets are uploaded on a second stream, segments grouped into chunks; the kernels of

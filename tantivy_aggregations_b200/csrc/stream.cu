@@ -59,6 +59,9 @@ struct SegDesc {
     uint64_t minv[ST_MAXCOLS];
     uint32_t nb[ST_MAXCOLS];
     const uint8_t* bits_ptr[ST_MAXBITS];  // 0 = main docset, 1 = deleted, 2+i = filter docset of pred i
+    // bytes readable behind bits_ptr (a multiple of 16): whole tiles for device bitsets; ceil16(max_doc / 8) for a
+    // page-locked HOST bitset that the producer reads in place over PCIe (no staging copy, exec.cu normalise_docset)
+    uint32_t bits_len[ST_MAXBITS];
     uint64_t pred_lo[ST_MAXPRED], pred_hi[ST_MAXPRED];
 };
 struct SGroup {
@@ -312,12 +315,19 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             const uint32_t flags = Sg->flags;
             TileDesc* T = tdesc + stage;
             uint8_t* base = stages + (size_t)stage * p.stage_bytes;
+            uint32_t issued = 0;  // bytes this lane asked the TMA unit for
             if (lane < (uint32_t)p.n_cols) {
                 uint32_t cb = (ST_TILE / 8) * Sg->nb[lane];
                 if (cb) tma_bulk_g2s(base + p.soff_col[lane], Sg->col_ptr[lane] + (size_t)lt * cb, cb, full + stage);
+                issued = cb;
             } else if (lane >= 8 && lane < 8 + ST_MAXBITS) {
                 uint32_t b = lane - 8;
-                if (flags & (1u << b)) tma_bulk_g2s(base + p.soff_bits + 256 * b, Sg->bits_ptr[b] + (size_t)lt * (ST_TILE / 8), ST_TILE / 8, full + stage);
+                if (flags & (1u << b)) {
+                    const uint32_t at = lt * (ST_TILE / 8), len = Sg->bits_len[b];
+                    const uint32_t cb = len > at ? min((uint32_t)(ST_TILE / 8), len - at) : 0u;  // a host bitset ends inside its last tile
+                    if (cb) tma_bulk_g2s(base + p.soff_bits + 256 * b, Sg->bits_ptr[b] + at, cb, full + stage);
+                    issued = cb;
+                }
             } else if (lane == 16) {
                 T->n_valid = (uint32_t)min((uint64_t)ST_TILE, (uint64_t)Sg->max_doc - (uint64_t)lt * ST_TILE);
                 T->flags = flags;
@@ -329,9 +339,8 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 uint32_t i = lane - 24;
                 if (i < (uint32_t)p.n_preds) { T->pred_lo[i] = Sg->pred_lo[i]; T->pred_hi[i] = Sg->pred_hi[i]; }
             }
-            __syncwarp();
+            const uint32_t bytes = __reduce_add_sync(0xffffffffu, issued);
             if (lane == 0) {
-                uint32_t bytes = Sg->tile_bytes;
                 if (bytes) mbar_expect_tx(full + stage, bytes);
                 else mbar_arrive(full + stage);  // nothing to stage (count over AllQuery)
             }
@@ -1373,8 +1382,12 @@ static int stream_launch(ExecState& es, bool first_launch) {
             }
             if (fpos) d.flags |= SF_FPOS;
         }
-        if (hs.main.kind == DS_BITSET) { d.flags |= SF_MAIN_BITS; d.bits_ptr[0] = (const uint8_t*)hs.main.words; narrowing = true; }
-        if (hs.has_deletes) { d.flags |= SF_DELETES; d.bits_ptr[1] = (const uint8_t*)hs.deleted; narrowing = true; }
+        const uint32_t padded = (uint32_t)((((uint64_t)hs.max_doc + ST_TILE - 1) / ST_TILE) * (ST_TILE / 8));
+        if (hs.main.kind == DS_BITSET) {
+            d.flags |= SF_MAIN_BITS; d.bits_ptr[0] = (const uint8_t*)hs.main.words; narrowing = true;
+            d.bits_len[0] = hs.main.n ? (uint32_t)hs.main.n : padded;
+        }
+        if (hs.has_deletes) { d.flags |= SF_DELETES; d.bits_ptr[1] = (const uint8_t*)hs.deleted; d.bits_len[1] = padded; narrowing = true; }
         for (int pi = 0; pi < sp.n_preds; pi++) {
             int src = pred_src[pi];
             if (src == -2) { d.pred_lo[pi] = hs.main.lo; d.pred_hi[pi] = hs.main.hi; }
@@ -1382,7 +1395,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
             else {
                 const DevDocset& fd = hs.filters[src];
                 if (sp.pred_type[pi] == PR_RANGE) { d.pred_lo[pi] = fd.lo; d.pred_hi[pi] = fd.hi; }
-                else if (fd.kind == DS_BITSET) { d.flags |= SF_PRED_BITS0 << pi; d.bits_ptr[2 + pi] = (const uint8_t*)fd.words; }
+                else if (fd.kind == DS_BITSET) { d.flags |= SF_PRED_BITS0 << pi; d.bits_ptr[2 + pi] = (const uint8_t*)fd.words; d.bits_len[2 + pi] = fd.n ? (uint32_t)fd.n : padded; }
                 else if (fd.kind != DS_ALL) d.flags |= SF_PRED_NONE0 << pi;
             }
         }

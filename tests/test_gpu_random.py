@@ -247,3 +247,31 @@ def test_filter_tables_and_level_filters_on_integer_columns(ctx):
         finally:
             ctx.set_path(F.PATH_AUTO)
         assert_fruit_equal(got, want, F64_SUM_RTOL, name)
+
+
+def test_page_locked_docsets_are_read_in_place(ctx, world):
+    """Page-locked, 16-byte aligned host bitsets (main docset and filter_agg docsets) are pulled over PCIe by the streaming
+    kernel's TMA producer without a staging copy; the result must equal the staged-copy path and the oracle, including
+    segments whose bitset ends inside its last tile."""
+    import torch
+    corpus, searcher, ox = world
+    rng = np.random.default_rng(23)
+    bits, pinned_bits, keep = {}, {}, []
+    for i, s in enumerate(corpus.segs):
+        m = rng.random(s.max_doc) < 0.4
+        b = np.packbits(m.astype(np.uint8), bitorder="little")
+        bits[i] = b
+        t = torch.zeros((len(b) + 15) // 16 * 16 + 16, dtype=torch.uint8).pin_memory()
+        t.numpy()[:len(b)] = b
+        keep.append(t)
+        pinned_bits[i] = t.numpy()
+    for aname in ("scalars", "bench_shape", "terms", "hist", "post_filter", "terms_multi", "nested"):
+        mk = aggs()[aname]
+        want, _, _ = ox.search(ta.BitsetQuery(bits), mk())
+        got = searcher.agg_search(ta.BitsetQuery(pinned_bits), mk())
+        assert_fruit_equal(got, want, F64_SUM_RTOL, aname)
+    # as a filter_agg docset
+    mk = lambda q: ta.filter_agg(q, (ta.count_agg(), ta.terms_agg_u64(CAT, (ta.count_agg(), ta.min_agg_f64(PRICE)))))
+    want, _, _ = ox.search(ta.AllQuery(), mk(ta.BitsetQuery(bits)))
+    got = searcher.agg_search(ta.AllQuery(), mk(ta.BitsetQuery(pinned_bits)))
+    assert_fruit_equal(got, want, F64_SUM_RTOL)
