@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <set>
 
 #include "exec.h"
 #include "host.h"
@@ -161,6 +162,10 @@ static int analyse(PlanMeta& m, uint32_t& pos, int parent, int scope, int depth)
     return 0;
 }
 
+// contexts that are alive (results are recycled into their context's pool on free)
+static std::mutex g_live_mu;
+static std::set<tagg_ctx*> g_live_ctx;
+
 extern "C" {
 
 uint32_t tagg_abi_version(void) { return TAGG_ABI_VERSION; }
@@ -205,12 +210,22 @@ int tagg_ctx_create(int device, tagg_ctx** out) {
         delete c;
         return tagg_fail(TAGG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     }
+    {
+        std::lock_guard<std::mutex> live(g_live_mu);
+        g_live_ctx.insert(c);
+    }
     *out = c;
     return 0;
 }
 
 int tagg_ctx_destroy(tagg_ctx* ctx) {
     if (!ctx) return 0;
+    {
+        std::lock_guard<std::mutex> live(g_live_mu);
+        g_live_ctx.erase(ctx);
+    }
+    for (auto r : ctx->result_pool) delete r;
+    ctx->result_pool.clear();
     cudaSetDevice(ctx->device);
     tagg_comm_destroy(ctx);
     for (auto c : ctx->call_pool) {
@@ -338,6 +353,16 @@ int tagg_execute_collective(const tagg_plan* plan, const tagg_segment_input* inp
 }
 
 int tagg_result_free(tagg_result* res) {
+    if (res && res->ctx) {  // recycle (bounded): the arrays keep their capacity for the next result
+        std::lock_guard<std::mutex> live(g_live_mu);
+        tagg_ctx* ctx = res->ctx;
+        if (g_live_ctx.count(ctx)) {  // (a result may outlive its context)
+            res->meta.reset();
+            res->pcts.clear();
+            std::lock_guard<std::mutex> g(ctx->mu);
+            if (ctx->result_pool.size() < 4) { ctx->result_pool.push_back(res); return 0; }
+        }
+    }
     delete res;
     return 0;
 }

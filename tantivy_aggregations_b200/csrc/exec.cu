@@ -706,7 +706,13 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         }
     }
 
-    auto* res = new tagg_result();
+    tagg_result* res = nullptr;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
+    }
+    if (!res) res = new tagg_result();
+    res->ctx = ctx;
     res->meta = plan->meta;
     rc = read_result(es, res);
     if (rc) {

@@ -213,8 +213,11 @@ int read_result(ExecState& es, tagg_result* res) {
     };
     const PlanMeta& m = *es.meta;
     size_t ns = es.scopes.size();
-    res->scopes.assign(ns, tagg_result::Scope());
-    res->slots.assign(es.slots.size(), tagg_result::Slot());
+    // (a recycled result keeps the capacity of its arrays: resize + clear, not assign)
+    res->scopes.resize(ns);
+    for (auto& sc : res->scopes) { sc.keys.clear(); sc.parents.clear(); }
+    res->slots.resize(es.slots.size());
+    for (auto& sl : res->slots) { sl.values.clear(); sl.seen.clear(); }
     std::vector<std::vector<uint32_t>> raw(ns);   // ascending raw bucket indices that exist
     std::vector<uint32_t*> d_raw(ns, nullptr);
 
