@@ -157,10 +157,7 @@ int comm_merge_arena(ExecState& es) {
     auto* s = (NcclState*)es.ctx->nccl;
     if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
     const PlanMeta& m = *es.meta;
-    for (auto& L : es.scopes)
-        if (L.mode != SCOPE_DENSE)
-            return tagg_fail(TAGG_ERR_UNSUPPORTED, "collective merge of hashed bucket tables is not implemented yet (dense key domains only)");
-    if (!m.pct_node.empty()) return tagg_fail(TAGG_ERR_UNSUPPORTED, "collective merge of percentiles is not implemented yet");
+    (void)m;
     if (es.arena_bytes * (size_t)es.ctx->n_ranks <= (256u << 20)) {
         uint8_t* gathered = nullptr;
         CUDA_TRY(cudaMallocAsync((void**)&gathered, es.arena_bytes * (size_t)es.ctx->n_ranks, es.st));
@@ -187,5 +184,111 @@ int comm_merge_arena(ExecState& es) {
     }
     NCCL_TRY(s, s->GroupEnd());
     CUDA_TRY(cudaStreamSynchronize(es.st));
+    return 0;
+}
+
+// ---- exchange of compact results -----------------------------------------------------------------------------------
+// Hashed bucket tables (slot positions differ from rank to rank) and percentile summaries cannot be reduced cell by cell:
+// every rank compacts its own result, the compact results are all-gathered (sizes first, then the padded byte images)
+// and folded on the host with PreparedAgg::merge in rank order (searcher.rs:93-96) — identical fruit on every rank.
+namespace {
+struct Writer {
+    std::vector<uint8_t> b;
+    void u64(uint64_t v) { size_t at = b.size(); b.resize(at + 8); memcpy(b.data() + at, &v, 8); }
+    void raw(const void* p, size_t n) { size_t at = b.size(); b.resize(at + ((n + 7) & ~(size_t)7)); if (n) memcpy(b.data() + at, p, n); }
+};
+struct Reader {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+    uint64_t u64() { uint64_t v = 0; if (p + 8 > end) { ok = false; return 0; } memcpy(&v, p, 8); p += 8; return v; }
+    template <typename T> void raw(std::vector<T>& out, size_t n) {
+        const size_t bytes = n * sizeof(T), padded = (bytes + 7) & ~(size_t)7;
+        if (p + padded > end) { ok = false; return; }
+        out.resize(n);
+        if (bytes) memcpy(out.data(), p, bytes);
+        p += padded;
+    }
+};
+void serialise(const tagg_result& r, Writer& w) {
+    w.u64(r.scopes.size());
+    for (auto& s : r.scopes) { w.u64(s.keys.size()); w.raw(s.keys.data(), s.keys.size() * 8); w.raw(s.parents.data(), s.parents.size() * 4); }
+    w.u64(r.slots.size());
+    for (auto& s : r.slots) { w.u64(s.values.size()); w.raw(s.values.data(), s.values.size() * 8); w.raw(s.seen.data(), s.seen.size()); }
+    w.u64(r.pcts.size());
+    for (auto& mp : r.pcts) {
+        w.u64(mp.size());
+        for (auto& kv : mp) {
+            w.u64(kv.first); w.u64(kv.second.n_total); w.u64(kv.second.ranks.size());
+            w.raw(kv.second.ranks.data(), kv.second.ranks.size() * 8);
+            w.raw(kv.second.value_bits.data(), kv.second.value_bits.size() * 8);
+        }
+    }
+}
+bool deserialise(Reader& rd, tagg_result& r) {
+    r.scopes.resize(rd.u64());
+    for (auto& s : r.scopes) { size_t n = rd.u64(); rd.raw(s.keys, n); rd.raw(s.parents, n); if (!rd.ok) return false; }
+    r.slots.resize(rd.u64());
+    for (auto& s : r.slots) { size_t n = rd.u64(); rd.raw(s.values, n); rd.raw(s.seen, n); if (!rd.ok) return false; }
+    r.pcts.resize(rd.u64());
+    for (auto& mp : r.pcts) {
+        size_t ne = rd.u64();
+        for (size_t i = 0; i < ne && rd.ok; i++) {
+            uint64_t bucket = rd.u64();
+            PctSummary& ps = mp[bucket];
+            ps.n_total = rd.u64();
+            size_t np = rd.u64();
+            rd.raw(ps.ranks, np);
+            rd.raw(ps.value_bits, np);
+        }
+    }
+    return rd.ok;
+}
+}  // namespace
+
+int comm_merge_results(ExecState& es, tagg_result* res) {
+    auto* s = (NcclState*)es.ctx->nccl;
+    if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
+    const int nr = es.ctx->n_ranks;
+    Writer w;
+    serialise(*res, w);
+    // sizes, then the padded images
+    uint64_t* d_sizes = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_sizes, (size_t)nr * 8, es.st));
+    es.temps.push_back(d_sizes);
+    const uint64_t mine = w.b.size();
+    CUDA_TRY(cudaMemcpyAsync(d_sizes + es.ctx->rank, &mine, 8, cudaMemcpyHostToDevice, es.st));
+    NCCL_TRY(s, s->AllGather(d_sizes + es.ctx->rank, d_sizes, 1, ncclUint64, s->comm, es.st));
+    std::vector<uint64_t> sizes(nr);
+    CUDA_TRY(cudaMemcpyAsync(sizes.data(), d_sizes, (size_t)nr * 8, cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    size_t slot = 0;
+    for (uint64_t x : sizes) slot = std::max<size_t>(slot, x);
+    slot = (slot + 255) & ~(size_t)255;
+    if (!slot) return 0;
+    uint8_t* d_all = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_all, slot * (size_t)nr, es.st));
+    es.temps.push_back(d_all);
+    CUDA_TRY(cudaMemcpyAsync(d_all + slot * (size_t)es.ctx->rank, w.b.data(), w.b.size(), cudaMemcpyHostToDevice, es.st));
+    NCCL_TRY(s, s->AllGather(d_all + slot * (size_t)es.ctx->rank, d_all, slot, ncclUint8, s->comm, es.st));
+    std::vector<uint8_t> all(slot * (size_t)nr);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, es.st));
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    tagg_result merged;
+    merged.meta = res->meta;
+    for (int r = 0; r < nr; r++) {
+        tagg_result part;
+        part.meta = res->meta;
+        Reader rd{all.data() + slot * (size_t)r, all.data() + slot * (size_t)r + sizes[r]};
+        if (!deserialise(rd, part)) return tagg_fail(TAGG_ERR_NCCL, "malformed result image from rank %d", r);
+        if (r == 0) { merged.scopes = std::move(part.scopes); merged.slots = std::move(part.slots); merged.pcts = std::move(part.pcts); }
+        else {
+            int rc = result_merge(&merged, &part);
+            if (rc) return rc;
+        }
+    }
+    res->scopes = std::move(merged.scopes);
+    res->slots = std::move(merged.slots);
+    res->pcts = std::move(merged.pcts);
     return 0;
 }

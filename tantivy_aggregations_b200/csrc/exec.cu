@@ -695,7 +695,10 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         }
     }
 
-    if (collective) {
+    // dense tables merge cell by cell on the device; hashed tables and percentile summaries as compact results (below)
+    bool arena_merge = collective && es.meta->pct_node.empty();
+    for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
+    if (arena_merge) {
         rc = comm_merge_arena(es);
         if (rc) return rc;
         size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
@@ -718,6 +721,13 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
     if (rc) {
         delete res;
         return rc;
+    }
+    if (collective && !arena_merge) {
+        rc = comm_merge_results(es, res);
+        if (rc) {
+            delete res;
+            return rc;
+        }
     }
     lap("read_result");
     res->kernel_ms = ms_total;

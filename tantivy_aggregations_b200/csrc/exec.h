@@ -122,6 +122,8 @@ int read_result(ExecState& es, tagg_result* res);
 // comm.cu: merge the accumulators of all ranks in place (dense scopes), before read_result
 int comm_agree_domains(ExecState& es, std::vector<uint64_t>& dom);
 int comm_merge_arena(ExecState& es);
+// hashed tables / percentile summaries: all-gather the compact results and fold them on the host in rank order
+int comm_merge_results(ExecState& es, tagg_result* res);
 // stream.cu: returns 1 if a streaming fast shape handled the plan, 0 if not applicable, <0 = -status
 int stream_try(ExecState& es);
 // mterms.cu: terms keyed by a multi-valued field / hashed key domain; returns members handled, <0 = -status

@@ -52,6 +52,7 @@ def build_corpus():
         s.col(2, F.F64, 1.0 + 100.0 * rng.random(n))
         s.col(3, F.I64, rng.integers(-50, 50, size=n, dtype=np.int64))
         s.mcol(4, F.U64, [list(rng.integers(0, 9, size=rng.integers(0, 4))) for _ in range(n)])
+        s.col(5, F.U64, (rng.integers(1, 6, size=n, dtype=np.uint64) << np.uint64(40)) | rng.integers(1, 30, size=n, dtype=np.uint64))  # sparse 43-bit keys: hashed table
         if n:
             s.deleted = rng.choice(n, size=n // 7, replace=False)
         segs.append(s)

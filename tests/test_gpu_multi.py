@@ -43,6 +43,41 @@ def _worker(rank, world, port, out_dir):
             ctx.set_path(path)
             got = local.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, collective=True)
             assert_fruit_equal(got, want, 1e-12, f"{name}/path{path}/rank{rank}")
+    # hashed bucket tables and percentile summaries: merged as compact results (all-gather + PreparedAgg::merge in rank order)
+    import numpy as np
+    from helpers import exact_rank_window
+    ctx.set_path(0)
+    sparse_key = lambda: ta.terms_agg_u64(5, (ta.count_agg(), ta.min_agg_f64(2)))
+    want, _, _ = ox.search(ta.AllQuery(), sparse_key(), mode=1, threads=2)
+    got = local.agg_search_with_executor(ta.AllQuery(), sparse_key(), ta.SINGLE_THREAD, collective=True)
+    assert_fruit_equal(got, want, 1e-12, f"hashed/rank{rank}")
+    pct_plan = lambda: (ta.count_agg(), ta.percentiles_agg_f64(2), ta.terms_agg_u64(1, ta.percentiles_agg_f64(2)))
+    cnt, pct, terms = local.agg_search_with_executor(ta.AllQuery(), pct_plan(), ta.SINGLE_THREAD, collective=True)
+    alive_vals, alive_cat = [], []
+    for sg in corpus.segs:
+        alive = np.ones(sg.max_doc, dtype=bool)
+        if sg.deleted is not None and sg.max_doc:
+            alive[np.asarray(sg.deleted)] = False
+        from tantivy_aggregations_b200 import codec
+        alive_vals.append(codec.code_to_f64(sg.cols[2][1])[alive])
+        alive_cat.append(sg.cols[1][1][alive])
+    vals, cats = np.concatenate(alive_vals), np.concatenate(alive_cat)
+    assert cnt == len(vals) == pct.n
+
+    def check(p, v):
+        srt = np.sort(v)
+        assert p.n == len(srt)
+        for qq in (0.01, 0.25, 0.5, 0.75, 0.99):
+            x = p.percentile(qq)
+            lo, hi = exact_rank_window(srt, x)
+            k = ta.ckms_target_rank(qq, len(srt))
+            band = 0.01 * qq * len(srt) + 1
+            assert lo <= hi and lo - band <= k <= hi + band, (qq, k, lo, hi)
+
+    check(pct, vals)
+    assert set(terms.res) == set(int(c) for c in np.unique(cats))
+    for c, p in terms.res.items():
+        check(p, vals[cats == c])
     dist.barrier()
     with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
         f.write("ok")
