@@ -146,22 +146,28 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
         if (xmax + 1 <= PCT_BINS) { mul = 0; n_bins = (uint32_t)(xmax + 1); }
         else { mul = (uint32_t)(((uint64_t)PCT_BINS << 32) / (xmax + 1)); n_bins = (uint32_t)((xmax * mul) >> 32) + 1; }
         auto bin_of = [&](uint64_t code) { const uint64_t x = (code - lo) >> shift; return mul ? (uint32_t)((x * mul) >> 32) : (uint32_t)x; };
+        // window by window (16 bins): a binary search finds the window's end in the sorted sample; only a window that
+        // looks too full is inspected bin by bin, to discount bins that hold a single distinct value
         bool ok = true;
-        uint64_t below = j, win_start_below = j, win_count = 0;
-        uint32_t win = 0;
+        uint64_t below = j;
         for (uint64_t a = j; a <= j_hi && ok;) {
-            const uint32_t bin = bin_of(smp[a]);
-            uint64_t b = a;
-            while (b <= j_hi && bin_of(smp[b]) == bin) b++;
-            if ((bin >> 4) != win) {
-                win = bin >> 4;
-                win_start_below = below;
-                win_count = 0;
+            const uint32_t win = bin_of(smp[a]) >> 4;
+            const uint64_t e = (uint64_t)(std::partition_point(smp.begin() + a, smp.begin() + j_hi + 1,
+                                                               [&](uint64_t code) { return (bin_of(code) >> 4) <= win; }) - smp.begin());
+            const double allowed = 16.0 * (PCT_EPS / 2) * (double)below;
+            if ((double)(e - a) > allowed) {
+                uint64_t spread = 0;
+                for (uint64_t b0 = a; b0 < e;) {
+                    const uint32_t bin = bin_of(smp[b0]);
+                    uint64_t b1 = b0;
+                    while (b1 < e && bin_of(smp[b1]) == bin) b1++;
+                    if (b1 - b0 < 2 || smp[b1 - 1] != smp[b0]) spread += b1 - b0;
+                    b0 = b1;
+                }
+                if ((double)spread > allowed) ok = false;
             }
-            if (b - a < 2 || smp[b - 1] != smp[a]) win_count += b - a;
-            if ((double)win_count > 16.0 * (PCT_EPS / 2) * (double)win_start_below) ok = false;
-            below += b - a;
-            a = b;
+            below += e - a;
+            a = e;
         }
         if (ok) { found = true; j_lo = j; }
     }
