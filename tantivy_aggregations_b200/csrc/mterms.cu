@@ -25,10 +25,10 @@
 #include "narrow.cuh"
 
 #define MT_SUB_THREADS 256
-#define MT_MAXSUB 3
+#define MT_MAXSUB 4
 #define MT_TILE 1024     // documents per sub-block tile
 #define MT_TILE_BITS 10
-#define MT_CHUNK 8192    // key occurrences expanded at a time
+#define MT_CHUNK 4096    // key occurrences expanded at a time
 #define MT_MAXGROUPS 2
 #define MT_MAXPRED NARROW_MAXPRED
 #define MT_MAXCOUNTS 2
