@@ -4,7 +4,8 @@
 //
 // The reference touches a bucket once per VALUE OCCURRENCE of the key field and lets the nested leaves
 // collect the DOCUMENT each time, i.e. sum_agg_f64s under terms_agg_u64s adds all of the document's
-// values once per key occurrence.  Here a sub-block of 256 threads owns a tile of 1024 documents:
+// values once per key occurrence.  Here a sub-block of 256 threads (up to 4 per CTA, independent, named barriers) owns
+// a tile of 1024 documents:
 //   doc phase    one thread per document: docset / deletes / predicates, the document's key range
 //                [idx[d], idx[d+1]) and its leaf contribution folded ONCE (sum / min / max over the
 //                document's values) into shared memory;

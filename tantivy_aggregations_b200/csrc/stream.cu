@@ -1,28 +1,30 @@
-// stream.cu — the streaming fast path: K1 (scan_reduce), K2 (terms, dense tables), K3 (histogram).
+// stream.cu — the streaming fast path: K1 (scan_reduce), K2 (terms), K3 (histogram), K4 (percentile rank bins).
 //
 // One persistent launch covers every segment of the call.  The unit of work is a TILE of 2048
 // consecutive documents of one segment.  For each tile the bytes of every referenced column
 // (256 * num_bits bytes, contiguous and 16-byte aligned in the bit-packed layout) and 256 bytes of
-// every bitset (docset, filter_agg docsets, delete bitset) are staged into shared memory by TMA bulk
-// copies (cp.async.bulk + mbarrier) through a 3-stage ring, so HBM is read exactly once, fully
-// coalesced, while the SM unpacks the previous tile from shared memory.
+// every bitset (docset, filter_agg docsets, delete bitset — a page-locked HOST bitset is pulled in place
+// over PCIe) are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) through a 2-4
+// stage ring by a producer warp, so HBM is read exactly once, fully coalesced, while 8 consumer warps per
+// group unpack the previous tile from shared memory.
 //
-// Per tile each warp owns 256 documents = 8 bitset words:
+// Per tile each consumer warp owns 256 documents = 8 bitset words:
 //   phase 1  lanes 0..7 AND the staged bitset words (docset, ~deletes, filter docsets) of "their"
-//            word into a match mask; value predicates (post_filter / COLUMN_RANGE) are evaluated per
-//            document and folded in with ballots;
-//   phase 2  the set bits are COMPACTED into a per-warp queue of document indices (warp scan of the
-//            popcounts + one predicated shared store per word);
+//            word into a match mask; value predicates (post_filter / COLUMN_RANGE) are folded in — narrow
+//            columns on packed 64-bit windows in the delta domain, wide ones per document with ballots;
+//   phase 2  the set bits are COMPACTED into a per-warp queue of document indices;
 //   phase 3  full warps drain the queue: only matched documents pay the unpack of key / value
 //            columns and the table updates (the reference pays a hash probe per matched doc,
 //            terms.rs:127-132; the doc-stream narrowing is filter.rs:100-122 / post_filter.rs:245-249).
-// With nothing narrowing the doc stream (AllQuery, no deletes) phase 2 is skipped.
+// With nothing narrowing the doc stream (AllQuery, no deletes) phase 2 is skipped and the unpack is
+// strength-reduced (a lane's 8 values sit exactly num_bits words apart).
 //
-// Root metrics live in registers and are reduced by warp shuffles; bucket metrics go to dense tables
-// in global memory (L2-resident): counts / sums with RED atomics, min / max with a cached
-// check-before-atomic (cells only move monotonically, so a stale read can only cause a redundant
-// atomic, never a wrong skip).  The kernel is a template over the number of root / bucket column
-// groups so every per-tile column descriptor lives in registers.
+// Root metrics live in registers (CT shapes: on the packed deltas) and are reduced by warp shuffles.  Bucket
+// metrics go, depending on what fits the 227 KB of shared memory, to CTA-private exact tables, to CTA-private
+// u32 filter tables in front of exact global cells, or to global tables (L2 RED atomics) behind a 4-bit level
+// filter and a presence bitmap — see SParams and DESIGN.md §4.  The kernel is a template over the bucket mode
+// and the number of root / bucket column groups so every column descriptor lives in registers; the hot
+// configurations get compile-time op masks (CT shapes).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
