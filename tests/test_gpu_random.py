@@ -275,3 +275,32 @@ def test_page_locked_docsets_are_read_in_place(ctx, world):
     want, _, _ = ox.search(ta.AllQuery(), mk(ta.BitsetQuery(bits)))
     got = searcher.agg_search(ta.AllQuery(), mk(ta.BitsetQuery(pinned_bits)))
     assert_fruit_equal(got, want, F64_SUM_RTOL)
+
+
+@pytest.mark.parametrize("start,interval", [(-37.5, 3.7), (0.1, 0.3), (1e-3, 12.5)])
+def test_histogram_boundary_table_is_bit_exact(ctx, start, interval):
+    """Large inputs take the boundary-table histogram (multiply + exact code boundaries instead of the IEEE division of
+    histogram.rs:146): the bucket of every value must equal floor((v - start) / interval) computed in IEEE doubles,
+    including values a few ulps around every bucket edge, values below start (skipped) and -0.0."""
+    rng = np.random.default_rng(31)
+    n = 4_400_000  # > 2048 tiles: the table path
+    vals = rng.normal(0.0, 20.0, size=n) if start < 0 else np.abs(rng.normal(0.0, 20.0, size=n))
+    # plant the edges themselves and their neighbours
+    edges = start + interval * np.arange(0, 60, dtype=np.float64)
+    planted = np.concatenate([np.nextafter(edges, -np.inf), edges, np.nextafter(edges, np.inf), [-0.0, 0.0, start]])
+    vals[:len(planted)] = planted
+    seg = SegSpec(n).col(PRICE, F.F64, vals)
+    searcher = Corpus([seg]).build_gpu(ctx)
+    hist, cnt = searcher.agg_search(ta.AllQuery(), (ta.histogram_agg_f64(PRICE, start, interval, ta.count_agg()), ta.count_agg()))
+    assert cnt == n
+    d = vals - start
+    ok = ~(d < 0.0)
+    ords, counts = np.unique(np.floor(d[ok] / interval).astype(np.int64), return_counts=True)
+    assert dict(hist._buckets) == {int(o): int(c) for o, c in zip(ords, counts)}
+    # and the generic (division) path agrees
+    ctx.set_path(F.PATH_GENERIC)
+    try:
+        hist2 = searcher.agg_search(ta.AllQuery(), ta.histogram_agg_f64(PRICE, start, interval, ta.count_agg()))
+    finally:
+        ctx.set_path(F.PATH_AUTO)
+    assert dict(hist2._buckets) == dict(hist._buckets)
