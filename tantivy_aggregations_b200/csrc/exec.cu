@@ -624,6 +624,14 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             handled = stream_try(es);
             if (handled < 0) return -handled;
         }
+        // a rank-bin pass that was planned but whose launch did not happen (its member is not flagged) must not shadow
+        // the exact path
+        for (size_t k = 0; k < es.meta->pct_node.size() && k < 4; k++)
+            if (es.rank[k].active && !es.skip[es.meta->pct_node[k]]) {
+                if (es.rank[k].d_block) cudaFreeAsync(es.rank[k].d_block, es.st);
+                if (es.rank[k].d_tail) cudaFreeAsync(es.rank[k].d_tail, es.st);
+                es.rank[k] = ExecState::RankState();
+            }
         int mt = 0;
         if (handled != 1 && ctx->path != 1) {  // K5: terms keyed by multi-valued / hashed fields
             mt = mterms_try(es);
