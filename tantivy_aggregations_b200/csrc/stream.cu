@@ -757,7 +757,8 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 }
             };
             // the non-negative fast path is instantiated where it pays: CT shapes and histograms
-            constexpr bool HAS_POS = (SH::BOPS >= 0 || SH::ROPS >= 0 || BUCKET == BK_HIST) && BUCKET != BK_RANK;
+            // (only where a value is converted to f64: sums and histogram keys; min / max never need it)
+            constexpr bool HAS_POS = ((SH::BOPS >= 0 && (SH::BOPS & OPB_SUM)) || (SH::ROPS >= 0 && (SH::ROPS & OPB_SUM)) || BUCKET == BK_HIST) && BUCKET != BK_RANK;
             auto run = [&](auto U_, auto CHECK_, const uint32_t* dl, const bool* act_in) {
                 if (HAS_POS && fpos) process(U_, CHECK_, std::true_type{}, dl, act_in);
                 else process(U_, CHECK_, std::false_type{}, dl, act_in);
