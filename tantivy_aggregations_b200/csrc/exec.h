@@ -79,6 +79,8 @@ struct ExecState {
     struct RankState {
         bool active = false;
         uint64_t lo = 0, span = 0;   // binned codes: lo <= code < lo + span
+        bool linear = false;         // bins equal-width in the VALUE: bin = (uint32)((f64(code) - f_lo) * f_scale), clamped
+        double f_lo = 0, f_scale = 0;
         uint32_t shift = 0, mul = 0, n_bins = 0;  // bin = umulhi((code - lo) >> shift, mul), or (code - lo) >> shift if mul == 0
         uint8_t* d_block = nullptr;  // [tail counters 16 B][count u64 x n_bins][min][max][present u8 x n_bins]
         uint64_t *d_count = nullptr, *d_min = nullptr, *d_max = nullptr;

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "exec.h"
@@ -131,51 +132,78 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
     const uint64_t hi = top == ~0ull ? top : top + 1;
     // lo = the smallest sample quantile for which, going by the sample, every window of 16 bins holds fewer than
     // 16 * eps/2 of the values below it (bins with a single distinct value cost no precision and do not count)
+    // Two monotone binnings are tried: equal-width in CODE space (f64 codes are log-like in the value: right for positive,
+    // heavy-tailed data such as prices) and, if that cannot meet the bound, equal-width in VALUE space (right for signed or
+    // symmetric data, whose codes around zero span every exponent)
     uint64_t lo = 0, span = 0;
     uint32_t shift = 0, mul = 0, n_bins = 0;
+    double f_lo = 0.0, f_scale = 0.0;
+    bool linear = false;
     uint64_t j_lo = 0;
     bool found = false;
-    for (uint64_t j = std::max<uint64_t>(64, mm / 1024); j <= mm / 8 && !found; j += std::max<uint64_t>(1, j / 4)) {
-        lo = smp[j];
-        if (hi <= lo) break;
-        span = hi - lo;
-        // monotone binning: bin = umulhi(d >> shift, mul) (or d itself when the span is at most PCT_BINS codes)
-        const uint32_t bits = 64 - (uint32_t)__builtin_clzll(span - 1 ? span - 1 : 1);
-        shift = bits > 32 ? bits - 32 : 0;
-        const uint64_t xmax = (span - 1) >> shift;
-        if (xmax + 1 <= PCT_BINS) { mul = 0; n_bins = (uint32_t)(xmax + 1); }
-        else { mul = (uint32_t)(((uint64_t)PCT_BINS << 32) / (xmax + 1)); n_bins = (uint32_t)((xmax * mul) >> 32) + 1; }
-        auto bin_of = [&](uint64_t code) { const uint64_t x = (code - lo) >> shift; return mul ? (uint32_t)((x * mul) >> 32) : (uint32_t)x; };
-        // window by window (16 bins): a binary search finds the window's end in the sorted sample; only a window that
-        // looks too full is inspected bin by bin, to discount bins that hold a single distinct value
-        bool ok = true;
-        uint64_t below = j;
-        for (uint64_t a = j; a <= j_hi && ok;) {
-            const uint32_t win = bin_of(smp[a]) >> 4;
-            const uint64_t e = (uint64_t)(std::partition_point(smp.begin() + a, smp.begin() + j_hi + 1,
-                                                               [&](uint64_t code) { return (bin_of(code) >> 4) <= win; }) - smp.begin());
-            const double allowed = 16.0 * (PCT_EPS / 2) * (double)below;
-            if ((double)(e - a) > allowed) {
-                uint64_t spread = 0;
-                for (uint64_t b0 = a; b0 < e;) {
-                    const uint32_t bin = bin_of(smp[b0]);
-                    uint64_t b1 = b0;
-                    while (b1 < e && bin_of(smp[b1]) == bin) b1++;
-                    if (b1 - b0 < 2 || smp[b1 - 1] != smp[b0]) spread += b1 - b0;
-                    b0 = b1;
-                }
-                if ((double)spread > allowed) ok = false;
+    for (int mode = 0; mode < 2 && !found; mode++) {
+        linear = mode == 1;
+        const double v_top = code_to_f64_h(hi - 1);
+        if (linear && !std::isfinite(v_top)) break;
+        for (uint64_t j = std::max<uint64_t>(64, mm / 1024); j <= mm / 8 && !found; j += std::max<uint64_t>(1, j / 4)) {
+            lo = smp[j];
+            if (hi <= lo) break;
+            span = hi - lo;
+            if (linear) {
+                f_lo = code_to_f64_h(lo);
+                if (!std::isfinite(f_lo) || !(v_top > f_lo)) break;
+                f_scale = (double)PCT_BINS / (v_top - f_lo);
+                if (!std::isfinite(f_scale)) break;
+                n_bins = PCT_BINS;
+            } else {
+                // bin = umulhi(d >> shift, mul) (or d itself when the span is at most PCT_BINS codes)
+                const uint32_t bits = 64 - (uint32_t)__builtin_clzll(span - 1 ? span - 1 : 1);
+                shift = bits > 32 ? bits - 32 : 0;
+                const uint64_t xmax = (span - 1) >> shift;
+                if (xmax + 1 <= PCT_BINS) { mul = 0; n_bins = (uint32_t)(xmax + 1); }
+                else { mul = (uint32_t)(((uint64_t)PCT_BINS << 32) / (xmax + 1)); n_bins = (uint32_t)((xmax * mul) >> 32) + 1; }
             }
-            below += e - a;
-            a = e;
+            auto bin_of = [&](uint64_t code) -> uint32_t {
+                if (linear) {
+                    const double t = (code_to_f64_h(code) - f_lo) * f_scale;
+                    const uint32_t b = t > 0.0 ? (t < 4294967040.0 ? (uint32_t)t : 0xffffff00u) : 0u;
+                    return b < PCT_BINS ? b : PCT_BINS - 1;
+                }
+                const uint64_t x = (code - lo) >> shift;
+                return mul ? (uint32_t)((x * mul) >> 32) : (uint32_t)x;
+            };
+            // window by window (16 bins): a binary search finds the window's end in the sorted sample; only a window that
+            // looks too full is inspected bin by bin, to discount bins that hold a single distinct value
+            bool ok = true;
+            uint64_t below = j;
+            for (uint64_t a = j; a <= j_hi && ok;) {
+                const uint32_t win = bin_of(smp[a]) >> 4;
+                const uint64_t e = (uint64_t)(std::partition_point(smp.begin() + a, smp.begin() + j_hi + 1,
+                                                                   [&](uint64_t code) { return (bin_of(code) >> 4) <= win; }) - smp.begin());
+                const double allowed = 16.0 * (PCT_EPS / 2) * (double)below;
+                if ((double)(e - a) > allowed) {
+                    uint64_t spread = 0;
+                    for (uint64_t b0 = a; b0 < e;) {
+                        const uint32_t bin = bin_of(smp[b0]);
+                        uint64_t b1 = b0;
+                        while (b1 < e && bin_of(smp[b1]) == bin) b1++;
+                        if (b1 - b0 < 2 || smp[b1 - 1] != smp[b0]) spread += b1 - b0;
+                        b0 = b1;
+                    }
+                    if ((double)spread > allowed) ok = false;
+                }
+                below += e - a;
+                a = e;
+            }
+            if (ok) { found = true; j_lo = j; }
         }
-        if (ok) { found = true; j_lo = j; }
     }
     if (!found) return 0;
 
     ExecState::RankState& R = es.rank[k];
     R = ExecState::RankState();
     R.lo = lo; R.span = span; R.shift = shift; R.mul = mul; R.n_bins = n_bins;
+    R.linear = linear; R.f_lo = f_lo; R.f_scale = f_scale;
     // values outside [lo, hi): the sampled share below lo, plus what lies above the largest sampled value
     R.tail_cap = (uint64_t)(n_est * ((double)(j_lo + (mm - j_hi)) / (double)mm) * 1.5) + (uint64_t)(n_est / mm * 64) + (1u << 18);
     const size_t blk = 16 + (size_t)n_bins * 25;
@@ -221,7 +249,7 @@ int pct_rank_collect(ExecState& es, int k) {
     const uint64_t* mx = mn + nb;
     const uint64_t n_tail = tc[0], n_low = tc[1];
     static const bool trace = getenv("TAGG_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[tagg] rank bins: lo=%016llx span=%016llx shift=%u bins=%u tail=%llu (low %llu) cap=%llu\n", (unsigned long long)R.lo,
+    if (trace) fprintf(stderr, "[tagg] rank bins (%s): lo=%016llx span=%016llx shift=%u bins=%u tail=%llu (low %llu) cap=%llu\n", R.linear ? "value space" : "code space", (unsigned long long)R.lo,
                        (unsigned long long)R.span, R.shift, nb, (unsigned long long)n_tail, (unsigned long long)n_low, (unsigned long long)R.tail_cap);
     if (n_tail > R.tail_cap || n_low > n_tail) return 0;
     const uint64_t n_high = n_tail - n_low;

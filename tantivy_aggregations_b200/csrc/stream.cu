@@ -109,6 +109,8 @@ struct SParams {
     // codes outside are appended to an exact list (tail_count[0] = appended, [1] = those below rank_lo)
     uint64_t rank_lo, rank_span;
     uint32_t rank_shift, rank_mul;
+    uint32_t rank_linear;   // bins equal-width in the value instead: (uint32)((f64(code) - rank_flo) * rank_fscale), clamped
+    double rank_flo, rank_fscale;
     uint64_t* tail_codes;
     unsigned long long* tail_count;
     uint64_t tail_cap;
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         // CT root shape (one f64 column, compile-time ops): min / max run on the packed deltas and are folded into
         // the code domain only when the column's min_value changes (segment change); the sum adds delta + constant
         constexpr bool CTROOT = SH::ROPS >= 0 && NRG == 1;
+        constexpr bool RANK_LINEAR = BUCKET == BK_RANK && SH::ROPS == -2;  // value-space rank bins (pct.cu)
         uint64_t dmin = ~0ull, dmax = 0, cminv = 0;
         bool fseen = false;
         auto fold_root = [&]() {
@@ -626,8 +629,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             } else if (BUCKET == BK_RANK) {
                                 const uint64_t code = tget(kc, dl[u]);
                                 const uint64_t d = code - p.rank_lo;  // below rank_lo: wraps above the span
-                                rel[u] = (uint32_t)(d >> p.rank_shift);
-                                if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
+                                if (RANK_LINEAR) {  // (its own instantiation: the rank kernels are instruction-cache sensitive)
+                                    rel[u] = min(__double2uint_rz(__dmul_rn(__dsub_rn(c2f(code), p.rank_flo), p.rank_fscale)), dom_size32 - 1u);
+                                } else {
+                                    rel[u] = (uint32_t)(d >> p.rank_shift);
+                                    if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
+                                }
                                 tail[u] = d >= p.rank_span;
                                 tail_code[u] = code;
                                 if (hb) {  // the fused histogram counts every matched value, binned or not
@@ -1037,7 +1044,7 @@ template <int ROPS>
 static stream_fn pick_ct_root(bool compact) {
     return compact ? (stream_fn)k_stream<Shp<BK_NONE, 0, 1, true, false, -1, ROPS>> : (stream_fn)k_stream<Shp<BK_NONE, 0, 1, false, false, -1, ROPS>>;
 }
-static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0, bool r0_f64) {
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0, bool r0_f64, bool rank_linear) {
     if (bucket == BK_TERMS && nbg == 1 && nrg == 0) {
         switch (bops0) {
             case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab);
@@ -1046,7 +1053,10 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
             case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab);
         }
     }
-    if (bucket == BK_RANK) return pick_ct_bucket<BK_RANK, (OPB_MIN | OPB_MAX)>(compact, true);
+    if (bucket == BK_RANK) {
+        if (rank_linear) return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -2>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -2>>;
+        return pick_ct_bucket<BK_RANK, (OPB_MIN | OPB_MAX)>(compact, true);
+    }
     if (bucket == BK_NONE && nrg == 1 && r0_f64) {
         switch (rops0) {
             case OPB_MIN: return pick_ct_root<OPB_MIN>(compact);
@@ -1269,6 +1279,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
             sp.dom_min = 0;
             sp.dom_size = R.n_bins;
             sp.rank_lo = R.lo; sp.rank_span = R.span; sp.rank_shift = R.shift; sp.rank_mul = R.mul;
+            sp.rank_linear = R.linear ? 1u : 0u; sp.rank_flo = R.f_lo; sp.rank_fscale = R.f_scale;
             sp.tail_codes = R.d_tail; sp.tail_count = R.d_tail_count; sp.tail_cap = R.tail_cap;
             sp.overflow_flag = (uint32_t*)(es.arena + es.off_overflow);
             sp.present = R.d_present;
@@ -1569,7 +1580,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
 
     // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
     int nrg_t = n_rgroups;
-    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u, n_rgroups && sp.rgroups[0].kind == TAGG_F64);
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u, n_rgroups && sp.rgroups[0].kind == TAGG_F64, sp.rank_linear != 0);
     static std::mutex attr_mu;
     static std::vector<stream_fn> attr_done;
     {

@@ -60,7 +60,7 @@ def test_rank_bin_percentiles(ctx, name):
     q = ta.BitsetQuery({0: np.packbits(m[:half].astype(np.uint8), bitorder="little"), 1: np.packbits(m[half:].astype(np.uint8), bitorder="little")})
     p, reader = searcher.agg_search_with_executor(q, ta.percentiles_agg_f64(PRICE), ta.SINGLE_THREAD, return_reader=True)
     check(p, vals[m])
-    if name in ("uniform_price", "lognormal", "discrete_ties"):
+    if name in ("uniform_price", "lognormal", "discrete_ties", "normal_signed", "narrow_normal"):
         assert reader.stats()["path"] == 2, "these distributions must stay on the one-pass streaming path"
     # together with a histogram and root metrics, AllQuery
     (cnt, hist, p2) = searcher.agg_search(ta.AllQuery(), (ta.count_agg(), ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)))
