@@ -149,6 +149,10 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
             lo = smp[j];
             if (hi <= lo) break;
             span = hi - lo;
+            {   // 32-bit rank word of a code inside [lo, hi): (code - lo) >> shift (also the kernel's min / max filter word)
+                const uint32_t bits = 64 - (uint32_t)__builtin_clzll(span - 1 ? span - 1 : 1);
+                shift = bits > 32 ? bits - 32 : 0;
+            }
             if (linear) {
                 f_lo = code_to_f64_h(lo);
                 if (!std::isfinite(f_lo) || !(v_top > f_lo)) break;
@@ -157,8 +161,6 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
                 n_bins = PCT_BINS;
             } else {
                 // bin = umulhi(d >> shift, mul) (or d itself when the span is at most PCT_BINS codes)
-                const uint32_t bits = 64 - (uint32_t)__builtin_clzll(span - 1 ? span - 1 : 1);
-                shift = bits > 32 ? bits - 32 : 0;
                 const uint64_t xmax = (span - 1) >> shift;
                 if (xmax + 1 <= PCT_BINS) { mul = 0; n_bins = (uint32_t)(xmax + 1); }
                 else { mul = (uint32_t)(((uint64_t)PCT_BINS << 32) / (xmax + 1)); n_bins = (uint32_t)((xmax * mul) >> 32) + 1; }

@@ -615,11 +615,13 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     uint32_t rel[U];
                     bool tail[U];
                     uint64_t tail_code[U];
+                    uint32_t rank_x[U];  // BK_RANK: 32-bit rank word of the code inside the binned range (doubles as the min / max filter word)
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         rel[u] = 0;
                         tail[u] = false;
                         tail_code[u] = 0;
+                        rank_x[u] = 0;
                         if (act[u]) {
                             if (BUCKET == BK_TERMS) {
                                 uint32_t lo, hi;
@@ -629,11 +631,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             } else if (BUCKET == BK_RANK) {
                                 const uint64_t code = tget(kc, dl[u]);
                                 const uint64_t d = code - p.rank_lo;  // below rank_lo: wraps above the span
+                                rank_x[u] = (uint32_t)(d >> p.rank_shift);
                                 if (RANK_LINEAR) {  // (its own instantiation: the rank kernels are instruction-cache sensitive)
                                     rel[u] = min(__double2uint_rz(__dmul_rn(__dsub_rn(c2f(code), p.rank_flo), p.rank_fscale)), dom_size32 - 1u);
                                 } else {
-                                    rel[u] = (uint32_t)(d >> p.rank_shift);
-                                    if (p.rank_mul) rel[u] = __umulhi(rel[u], p.rank_mul);
+                                    rel[u] = p.rank_mul ? __umulhi(rank_x[u], p.rank_mul) : rank_x[u];
                                 }
                                 tail[u] = d >= p.rank_span;
                                 tail_code[u] = code;
@@ -735,14 +737,14 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 }
                                 if (filt) {  // fire-and-forget: no load sits between the filter and the global RED
                                     if (ops & OPB_MIN) {
-                                        const uint32_t q = (uint32_t)((p.filt_hi[g] - code[u]) >> p.filt_shift[g]);
+                                        const uint32_t q = BUCKET == BK_RANK ? ~rank_x[u] : (uint32_t)((p.filt_hi[g] - code[u]) >> p.filt_shift[g]);
                                         if (q >= (uint32_t)cur_min[u]) {
                                             if (q > (uint32_t)cur_min[u]) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]), "r"(q) : "memory");
                                             atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
                                         }
                                     }
                                     if (ops & OPB_MAX) {
-                                        const uint32_t q = (uint32_t)((code[u] - p.filt_lo[g]) >> p.filt_shift[g]);
+                                        const uint32_t q = BUCKET == BK_RANK ? rank_x[u] : (uint32_t)((code[u] - p.filt_lo[g]) >> p.filt_shift[g]);
                                         if (q >= (uint32_t)cur_max[u]) {
                                             if (q > (uint32_t)cur_max[u]) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]), "r"(q) : "memory");
                                             atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
