@@ -146,8 +146,9 @@ struct DevScope {
 
 #define INVALID_BUCKET 0xFFFFFFFFu
 
+// multiplicative (Fibonacci) hashing: one 64-bit multiply in front of the probe load, slot = TOP bits of the product
 __device__ __forceinline__ uint64_t hash_key(uint64_t key, uint32_t parent) {
-    return mix64(key ^ ((uint64_t)parent * 0x9E3779B97F4A7C15ull));
+    return (key ^ ((uint64_t)parent * 0xD6E8FEB86659FD93ull)) * 0x9E3779B97F4A7C15ull;
 }
 
 // `entry(key).or_insert_with(create_fruit)` (terms.rs:129-130, histogram.rs:148-149):
@@ -161,7 +162,7 @@ __device__ __forceinline__ uint32_t scope_lookup(uint32_t* overflow, const DevSc
         return (uint32_t)idx;
     }
     uint64_t mask = sc.capacity - 1;
-    uint64_t h = hash_key(key, parent) & mask;
+    uint64_t h = hash_key(key, parent) >> __clzll(mask);  // capacity is a power of two >= 1024
     const bool root = sc.parent == 0;  // buckets of a top-level scope all hang off parent bucket 0
     for (uint64_t probes = 0; probes <= mask;) {
         // fast pre-check on the key cell alone (a key, once written, never changes; an all-zero cell is
