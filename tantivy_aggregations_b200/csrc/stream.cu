@@ -250,11 +250,12 @@ __device__ __forceinline__ uint64_t tget(const TCol& c, uint32_t i) {  // -> cod
 // Kernel shape.  RT shapes read the per-group op masks from the launch parameters (any flat plan);
 // CT shapes bake the op masks of the single bucket / root column group into the instantiation, so the
 // compiler drops every path the plan does not have (the hot configurations use these).
-template <int BUCKET_, int NBG_, int NRG_, bool COMPACT_, bool STAB_, int BOPS_ = -1, int ROPS_ = -1>
+template <int BUCKET_, int NBG_, int NRG_, bool COMPACT_, bool STAB_, int BOPS_ = -1, int ROPS_ = -1, int FILT_ = -1>
 struct Shp {
     static constexpr int BUCKET = BUCKET_, NBG = NBG_, NRG = NRG_;
     static constexpr bool COMPACT = COMPACT_, STAB = STAB_;
     static constexpr int BOPS = BOPS_, ROPS = ROPS_;
+    static constexpr int FILT = FILT_;  // filter tables: -1 decided by the launch parameters (RT shapes), 0 / 1 compiled in (CT shapes)
 };
 
 // Warp-specialised: a CTA is G groups of 9 warps — warp 0 of a group is the TMA producer, warps 1..8
@@ -363,7 +364,8 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         const uint32_t ops_b1 = NBG > 1 ? p.bgroups[1].ops : 0u, ops_b2 = NBG > 2 ? p.bgroups[2].ops : 0u;
         const uint32_t ops_r0 = SH::ROPS >= 0 ? (uint32_t)SH::ROPS : (NRG > 0 ? p.rgroups[0].ops : 0u);
         const uint32_t dom_size32 = (uint32_t)p.dom_size;
-        const bool filt = STAB && p.tab_filt != 0;
+        const bool filt = SH::FILT < 0 ? (STAB && p.tab_filt != 0) : (SH::FILT == 1);
+        const bool two_counts = SH::BOPS < 0 && p.n_bcounts > 1;  // CT shapes are picked for at most one bucket count
 
         // per-thread root accumulators
         uint64_t rsum[NRG ? NRG : 1], rmin[NRG ? NRG : 1], rmax[NRG ? NRG : 1];
@@ -678,10 +680,10 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                         if (act[u]) {
                             if (STAB) {
                                 asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_tab_count[0] + 4 * rel[u]) : "memory");
-                                if (p.n_bcounts > 1) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_tab_count[1] + 4 * rel[u]) : "memory");
+                                if (two_counts) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_saddr + p.soff_tab_count[1] + 4 * rel[u]) : "memory");
                             } else {
                                 if (p.n_bcounts > 0) atomicAdd((unsigned long long*)(p.bcount_acc[0] + rel[u]), 1ull);
-                                if (p.n_bcounts > 1) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel[u]), 1ull);
+                                if (two_counts) atomicAdd((unsigned long long*)(p.bcount_acc[1] + rel[u]), 1ull);
                                 if (p.soff_present_bits) {  // no count names the bucket: CTA bitmap, flushed once at the end
                                     const uint32_t wa = smem_saddr + p.soff_present_bits + 4 * (rel[u] >> 5), bit = 1u << (rel[u] & 31);
                                     if (!(lds32(wa) & bit)) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(bit) : "memory");
@@ -1038,26 +1040,27 @@ static stream_fn pick_nbg(int nbg, int nrg, bool compact, bool stab) {
 }
 // compile-time-op-mask shapes for the hot configurations (one bucket value column or one root column)
 template <int BUCKET, int BOPS>
-static stream_fn pick_ct_bucket(bool compact, bool stab) {
-    if (stab) return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, true, BOPS>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, true, BOPS>>;
-    return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, false, BOPS>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, false, BOPS>>;
+static stream_fn pick_ct_bucket(bool compact, bool stab, bool filt) {
+    if (stab && filt) return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, true, BOPS, -1, 1>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, true, BOPS, -1, 1>>;
+    if (stab) return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, true, BOPS, -1, 0>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, true, BOPS, -1, 0>>;
+    return compact ? (stream_fn)k_stream<Shp<BUCKET, 1, 0, true, false, BOPS, -1, 0>> : (stream_fn)k_stream<Shp<BUCKET, 1, 0, false, false, BOPS, -1, 0>>;
 }
 template <int ROPS>
 static stream_fn pick_ct_root(bool compact) {
     return compact ? (stream_fn)k_stream<Shp<BK_NONE, 0, 1, true, false, -1, ROPS>> : (stream_fn)k_stream<Shp<BK_NONE, 0, 1, false, false, -1, ROPS>>;
 }
-static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0, bool r0_f64, bool rank_linear) {
-    if (bucket == BK_TERMS && nbg == 1 && nrg == 0) {
+static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool stab, uint32_t bops0, uint32_t rops0, bool r0_f64, bool rank_linear, bool filt, int n_bcounts) {
+    if (bucket == BK_TERMS && nbg == 1 && nrg == 0 && n_bcounts <= 1) {
         switch (bops0) {
-            case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab);
-            case OPB_MAX: return pick_ct_bucket<BK_TERMS, OPB_MAX>(compact, stab);
-            case OPB_SUM: return pick_ct_bucket<BK_TERMS, OPB_SUM>(compact, stab);
-            case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab);
+            case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab, filt);
+            case OPB_MAX: return pick_ct_bucket<BK_TERMS, OPB_MAX>(compact, stab, filt);
+            case OPB_SUM: return pick_ct_bucket<BK_TERMS, OPB_SUM>(compact, stab, filt);
+            case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab, filt);
         }
     }
     if (bucket == BK_RANK) {
-        if (rank_linear) return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -2>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -2>>;
-        return pick_ct_bucket<BK_RANK, (OPB_MIN | OPB_MAX)>(compact, true);
+        if (rank_linear) return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -2, 1>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -2, 1>>;
+        return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -1, 1>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -1, 1>>;
     }
     if (bucket == BK_NONE && nrg == 1 && r0_f64) {
         switch (rops0) {
@@ -1582,7 +1585,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
 
     // compaction pays when documents are filtered out; with nothing narrowing the stream it is pure overhead
     int nrg_t = n_rgroups;
-    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u, n_rgroups && sp.rgroups[0].kind == TAGG_F64, sp.rank_linear != 0);
+    stream_fn fn = pick_kernel(bucket_mode, n_bgroups, nrg_t, narrowing, stab, n_bgroups ? sp.bgroups[0].ops : 0u, n_rgroups ? sp.rgroups[0].ops : 0u, n_rgroups && sp.rgroups[0].kind == TAGG_F64, sp.rank_linear != 0, sp.tab_filt != 0, sp.n_bcounts);
     static std::mutex attr_mu;
     static std::vector<stream_fn> attr_done;
     {
