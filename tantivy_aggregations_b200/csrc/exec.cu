@@ -689,6 +689,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         }
         if (overflow == 3) es.no_rank = true;  // the rank bins could not resolve this distribution: exact path
         if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
+        if (overflow == 4) return tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
         if (attempt >= 6) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
         // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
         if (overflow == 1) es.hash_shift += 2;

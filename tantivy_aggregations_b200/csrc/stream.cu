@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             }
             dmin = ~0ull; dmax = 0; fseen = false;
         };
+        bool bad_key = false;  // a key outside the domain its column header declares (corrupt input)
         uint32_t matched = 0;  // every lane holds the warp's count
 
         // BK_RANK: this warp's buffer of out-of-range codes (the last ST_WARPS * ST_TBUF * 8 bytes of the group block)
@@ -629,7 +630,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 uint32_t lo, hi;
                                 tdelta(kc, dl[u], lo, hi);
                                 rel[u] = lo + krel;
-                                act[u] = rel[u] < dom_size32;
+                                // The key domain comes from the column headers, so a key cannot leave it.  Ragged batches keep
+                                // the per-document guard; full batches stay branch-free (clamp + a sticky error flag that fails
+                                // the call if a column ever contradicts its header)
+                                if (CHECK) { act[u] = rel[u] < dom_size32; }
+                                else { bad_key = bad_key || rel[u] >= dom_size32; rel[u] = min(rel[u], dom_size32 - 1u); }
                             } else if (BUCKET == BK_RANK) {
                                 const uint64_t code = tget(kc, dl[u]);
                                 const uint64_t d = code - p.rank_lo;  // below rank_lo: wraps above the span
@@ -888,6 +893,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         }
 
         if (CTROOT) fold_root();
+        if (BUCKET == BK_TERMS && bad_key && p.overflow_flag) *p.overflow_flag = 4u;
         if (BUCKET == BK_RANK && wtail) {
             // (the lambda lives inside the tile loop; same steps here for the last partial buffer)
             __syncwarp();
@@ -1426,6 +1432,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
     if (tiles_total > 0xffffffffull) return 0;
     sp.n_segs = (uint32_t)nseg;
     sp.n_tiles = (uint32_t)tiles_total;
+    sp.overflow_flag = (uint32_t*)(es.arena + es.off_overflow);
 
     // Option flags of the bucket slots coincide with bucket existence in the flat shape: alias them
     if (bucket_mode != BK_NONE) {
