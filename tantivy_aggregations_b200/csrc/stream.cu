@@ -1064,6 +1064,10 @@ static stream_fn pick_kernel(int bucket, int nbg, int nrg, bool compact, bool st
             case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab, filt);
         }
     }
+    if (bucket == BK_HIST && nbg == 0 && nrg == 0 && n_bcounts <= 1) {  // histogram_agg_f64(field, interval, count_agg())
+        if (stab) return compact ? (stream_fn)k_stream<Shp<BK_HIST, 0, 0, true, true, 0, -1, 0>> : (stream_fn)k_stream<Shp<BK_HIST, 0, 0, false, true, 0, -1, 0>>;
+        return compact ? (stream_fn)k_stream<Shp<BK_HIST, 0, 0, true, false, 0, -1, 0>> : (stream_fn)k_stream<Shp<BK_HIST, 0, 0, false, false, 0, -1, 0>>;
+    }
     if (bucket == BK_RANK) {
         if (rank_linear) return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -2, 1>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -2, 1>>;
         return compact ? (stream_fn)k_stream<Shp<BK_RANK, 1, 0, true, true, (OPB_MIN | OPB_MAX), -1, 1>> : (stream_fn)k_stream<Shp<BK_RANK, 1, 0, false, true, (OPB_MIN | OPB_MAX), -1, 1>>;
