@@ -50,17 +50,23 @@ __global__ void k_pack(const uint64_t* __restrict__ codes, uint64_t n, uint64_t 
     }
 }
 
-__global__ void k_ids_to_bitset(const uint32_t* __restrict__ ids, uint64_t n, uint32_t* words) {
+// SORTED_IDS docset -> bitset.  The ids come from the caller: an id the segment does not have, or a list that is not
+// strictly ascending (what a tantivy scorer yields), is dropped / flagged instead of written out of bounds.
+__global__ void k_ids_to_bitset(const uint32_t* __restrict__ ids, uint64_t n, uint32_t* words, uint32_t max_doc, uint32_t* bad) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t d = ids[i];
+        if (d >= max_doc || (i > 0 && ids[i - 1] >= d)) {
+            if (bad) *bad = 1u;
+            if (d >= max_doc) continue;
+        }
         atomicOr(words + (d >> 5), 1u << (d & 31));
     }
 }
 
-cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* words, cudaStream_t stream) {
+cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* words, uint32_t max_doc, uint32_t* bad, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     unsigned blocks = (unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
-    k_ids_to_bitset<<<blocks, 256, 0, stream>>>(ids, n, words);
+    k_ids_to_bitset<<<blocks, 256, 0, stream>>>(ids, n, words, max_doc, bad);
     return cudaGetLastError();
 }
 

@@ -34,7 +34,7 @@ __global__ void k_reduce_gathered(const uint8_t* __restrict__ gathered, uint8_t*
         ((uint64_t*)arena)[i] = v;
     }
     for (size_t i = b2 / 8 + t0; i < e2 / 8; i += stride) {  // f64 sums, folded in rank order
-        double v = 0.0;
+        double v = -0.0;  // the identity of the f64 sum cells (dev.cuh F64_NEG_ZERO_BITS)
         for (int r = 0; r < n_ranks; r++) v = __dadd_rn(v, ((const double*)(gathered + (size_t)r * arena_bytes))[i]);
         ((double*)arena)[i] = v;
     }

@@ -207,7 +207,19 @@ __device__ __forceinline__ uint32_t scope_lookup(uint32_t* overflow, const DevSc
 struct DevSlot {
     uint64_t* acc;   // per bucket of the enclosing scope.  MIN stores max(~code) so zero == empty identity
     uint8_t* seen;   // per bucket: Option is Some
+    // f64 MIN / MAX on a column that holds NaN or both signed zeros (exact PartialOrd fold of minmax.rs:97-106, exec.cu
+    // edge_scan): 3 * edge_cap cells of ~position (zero = none) — [first collected value | first -0.0 | first +0.0]
+    uint64_t* edge;
+    uint64_t edge_cap;
 };
+
+// f64 codes: the non-NaN values are exactly [code(-inf), code(+inf)]; the two zeros are adjacent
+#define CODE_NEG_INF 0x000FFFFFFFFFFFFFull
+#define CODE_POS_INF 0xFFF0000000000000ull
+#define CODE_NEG_ZERO 0x7FFFFFFFFFFFFFFFull
+#define CODE_POS_ZERO 0x8000000000000000ull
+#define F64_NEG_ZERO_BITS 0x8000000000000000ull  // identity of every f64 sum cell: x + -0.0 == x for all x (sum.rs:95-102)
+#define EDGE_POS_BITS 40                          // position of a collected value = segment index << 40 | doc / value index
 
 struct DevPlan {
     uint32_t n_nodes, n_scopes, n_slots, n_root_slots;

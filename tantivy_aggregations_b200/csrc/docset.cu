@@ -58,12 +58,17 @@ static int docset_to_device(const tagg_segment* seg, const tagg_docset* in, uint
             if (in->n && !in->data) return fail(tagg_fail(TAGG_ERR_BAD_ARG, "null doc-id list"));
             uint32_t* ids = nullptr;
             if (in->n) {
-                e = cudaMalloc(&ids, in->n * 4);
+                uint32_t bad = 0;  // [ids][flag]: an id >= max_doc or a list that is not strictly ascending
+                e = cudaMalloc(&ids, in->n * 4 + 16);
+                if (e == cudaSuccess) e = cudaMemsetAsync(ids + in->n, 0, 16, st);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(ids, in->data, in->n * 4, cudaMemcpyHostToDevice, st);
-                if (e == cudaSuccess) e = launch_ids_to_bitset(ids, in->n, w, st);
+                if (e == cudaSuccess) e = launch_ids_to_bitset(ids, in->n, w, seg->max_doc, ids + in->n, st);
                 ctx->launches++;
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, ids + in->n, 4, cudaMemcpyDeviceToHost, st);
                 cudaStreamSynchronize(st);
                 cudaFree(ids);
+                if (e == cudaSuccess && bad)
+                    return fail(tagg_fail(TAGG_ERR_BAD_ARG, "sorted-id docset: ids must be strictly ascending and < max_doc (%u)", seg->max_doc));
             }
             break;
         }

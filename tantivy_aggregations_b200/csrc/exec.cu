@@ -46,6 +46,10 @@ void ExecState::free_temps() {
     }
 }
 
+__global__ void k_fill_u64(uint64_t* __restrict__ dst, uint64_t n, uint64_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
 static inline uint64_t pow2ceil(uint64_t x) {
     uint64_t p = 1;
     while (p < x) p <<= 1;
@@ -134,6 +138,11 @@ static int normalise_docset(ExecState& es, const tagg_segment* seg, uint32_t seg
                 rc = dev_alloc(es, &scatter, words * 4);
                 if (rc) return rc;
                 CUDA_TRY(cudaMemsetAsync(scatter, 0, words * 4, es.st));
+                if (!es.d_bad_ids) {  // flag: an id >= max_doc / a list that is not strictly ascending
+                    rc = dev_alloc(es, &es.d_bad_ids, 16);
+                    if (rc) return rc;
+                    CUDA_TRY(cudaMemsetAsync(es.d_bad_ids, 0, 16, es.st));
+                }
             }
             if (in.n) es.uploads.push_back({ids, in.data, (size_t)in.n * 4, seg_index, scatter, in.n, slot});
             es.alg_bytes += in.n * 4;
@@ -315,7 +324,7 @@ static int issue_uploads(ExecState& es) {
             auto& u = es.uploads[i];
             CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, up));
             if (u.scatter_words) {
-                CUDA_TRY(launch_ids_to_bitset((const uint32_t*)u.dst, u.scatter_n, u.scatter_words, up));
+                CUDA_TRY(launch_ids_to_bitset((const uint32_t*)u.dst, u.scatter_n, u.scatter_words, es.segs[u.seg]->max_doc, es.d_bad_ids, up));
                 es.ctx->launches++;
                 es.n_launches++;
             }
@@ -450,12 +459,57 @@ static int layout_arena(ExecState& es) {
         }
         es.cls_end[cls] = off;
     }
+    // exact f64 MIN / MAX (edge mode): position cells behind the reduction classes (never merged cell by cell)
+    for (size_t k = 0; k < es.slots.size(); k++) {
+        es.slots[k].off_edge = 0;
+        if (es.edge_exact && k < es.slot_edge.size() && es.slot_edge[k]) {
+            es.slots[k].off_edge = off;
+            off = align16(off + es.slots[k].capacity * 24);
+        }
+    }
     es.arena_bytes = off;
     void* p = nullptr;
     CUDA_TRY(cudaMallocAsync(&p, es.arena_bytes, es.st));
     es.arena = (uint8_t*)p;
     CUDA_TRY(cudaMemsetAsync(es.arena, 0, es.arena_bytes, es.st));
+    // f64 sum cells start at -0.0: x + -0.0 == x for every x, so the first value "replaces" (sum.rs:95-102) and a sum
+    // whose addends are all -0.0 stays -0.0 in whatever order the partial sums meet
+    if (es.cls_end[2] > es.cls_begin[2]) {
+        const uint64_t n = (es.cls_end[2] - es.cls_begin[2]) / 8;
+        k_fill_u64<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)es.ctx->sm_count * 4), 256, 0, es.st>>>(
+            (uint64_t*)(es.arena + es.cls_begin[2]), n, F64_NEG_ZERO_BITS);
+        CUDA_TRY(cudaGetLastError());
+        es.ctx->launches++;
+        es.n_launches++;
+    }
     return 0;
+}
+
+// Which f64 MIN / MAX leaves can see a NaN or both zeros?  The column headers are exact bounds of the stored codes.
+static void edge_scan(ExecState& es, bool* any_straddle, bool* any_nan) {
+    const PlanMeta& m = *es.meta;
+    es.slot_edge.assign(m.slot_node.size(), 0);
+    *any_straddle = *any_nan = false;
+    for (size_t k = 0; k < m.slot_node.size(); k++) {
+        const tagg_node& nd = m.nodes[m.slot_node[k]];
+        if (nd.kind != TAGG_F64 || (nd.op != TAGG_OP_MIN && nd.op != TAGG_OP_MAX)) continue;
+        uint8_t e = 0;
+        bool neg = false, pos = false;  // over all segments: a value <= -0.0 / >= +0.0 exists
+        for (const tagg_segment* sg : es.segs) {
+            const HostColumn* c = nullptr;
+            if (nd.multi) { auto it = sg->mcols.find(nd.field_id); if (it != sg->mcols.end()) c = &it->second.second; }
+            else { auto it = sg->cols.find(nd.field_id); if (it != sg->cols.end()) c = &it->second; }
+            if (!c || !c->n_values) continue;
+            const uint64_t lo = c->min_value, hi = c->min_value + c->amplitude;
+            if (lo < CODE_NEG_INF || hi > CODE_POS_INF) e = 2;
+            neg = neg || lo <= CODE_NEG_ZERO;
+            pos = pos || hi >= CODE_POS_ZERO;
+        }
+        if (!e && neg && pos) e = 1;
+        es.slot_edge[k] = e;
+        *any_straddle = *any_straddle || e == 1;
+        *any_nan = *any_nan || e == 2;
+    }
 }
 
 static int alloc_percentile_buffers(ExecState& es) {
@@ -532,8 +586,10 @@ static int build_dev_plan(ExecState& es) {
     for (size_t k = 0; k < es.slots.size(); k++) {
         P.slots[k].acc = (uint64_t*)(es.arena + es.slots[k].off_acc);
         P.slots[k].seen = es.arena + es.slots[k].off_seen;
+        P.slots[k].edge = es.slots[k].off_edge ? (uint64_t*)(es.arena + es.slots[k].off_edge) : nullptr;
+        P.slots[k].edge_cap = es.slots[k].capacity;
         int node = m.slot_node[k];
-        if (m.scope_of[node] == 0 && nroot < TAGG_MAX_ROOT_SLOTS) {
+        if (m.scope_of[node] == 0 && nroot < TAGG_MAX_ROOT_SLOTS && !P.slots[k].edge) {
             P.slot_root_index[k] = (int16_t)nroot;
             P.root_slot_nodes[nroot++] = (uint16_t)node;
         }
@@ -589,27 +645,38 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
 
     rc = issue_uploads(es);
     if (rc) return rc;
+    // f64 MIN / MAX: the order of the codes is the reference's PartialOrd fold except around NaN and the two zeros
+    bool edge_straddle = false, edge_nan = false;
+    edge_scan(es, &edge_straddle, &edge_nan);
+    es.edge_exact = edge_nan;  // a NaN in a column: exact path right away; zeros: only if the result turns out ambiguous
     float ms_total = 0;
+    tagg_result* res = nullptr;
+    bool arena_merge = false;
     for (int attempt = 0;; attempt++) {
         std::vector<uint64_t> dom, bounds;
         rc = scope_domains_local(es, dom, bounds);
         if (rc) return rc;
         if (collective) {
+            // one more agreed word: does ANY rank need the exact f64 MIN / MAX path?  (min-reduced: 0 = yes)
+            dom.push_back((edge_straddle || edge_nan) ? 0ull : 1ull);
             // the agreed domains only depend on the segments' column headers: remember them per segment set
             std::vector<const void*> key(es.segs.begin(), es.segs.end());
             std::vector<uint64_t> local = dom;
             bool hit = false;
             {
                 std::lock_guard<std::mutex> g(plan->mu);
-                if (plan->dom_key == key && plan->dom_local == local) { dom = plan->dom_agreed; hit = true; }
+                if (plan->dom_cache_ok && plan->dom_key == key && plan->dom_local == local) { dom = plan->dom_agreed; hit = true; }
             }
-            // every rank takes the same branch: the cache is filled by a collective call with the same inputs
+            // The cache is OFF unless the caller vouches that every rank reuses the plan on unchanged segment sets in
+            // lock-step (tagg_plan_set_collective_cache): a rank that hit while another missed would skip a collective
             if (!hit) {
                 rc = comm_agree_domains(es, dom);
                 if (rc) return rc;
                 std::lock_guard<std::mutex> g(plan->mu);
                 plan->dom_key = key; plan->dom_local = local; plan->dom_agreed = dom;
             }
+            if (dom.back() == 0) es.edge_exact = true;
+            dom.pop_back();
         }
         rc = finalize_scopes(es, dom, bounds);
         if (rc) return rc;
@@ -619,8 +686,11 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
 
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
         es.skip.assign(es.meta->nodes.size(), 0);
+        const bool fast_ok = ctx->path != 1 && !es.edge_exact;
+        if (es.edge_exact && ctx->path == 2)
+            return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over NaN or signed zeros runs on the exact (generic) path; path is forced to stream");
         int handled = 0;
-        if (ctx->path != 1) {
+        if (fast_ok) {
             handled = stream_try(es);
             if (handled < 0) return -handled;
         }
@@ -633,7 +703,7 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
                 es.rank[k] = ExecState::RankState();
             }
         int mt = 0;
-        if (handled != 1 && ctx->path != 1) {  // K5: terms keyed by multi-valued / hashed fields
+        if (handled != 1 && fast_ok) {  // K5: terms keyed by multi-valued / hashed fields
             mt = mterms_try(es);
             if (mt < 0) return -mt;
             if (mt > 0 && plan_fully_covered(es)) handled = 1;
@@ -649,8 +719,18 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             if (!es.uploads.empty())
                 for (uint32_t c = 0; c < es.n_chunks; c++) CUDA_TRY(cudaStreamWaitEvent(es.st, es.call->chunk_ev[c], 0));
             for (uint32_t i = 0; i < n_inputs; i++) {
-                CUDA_TRY(launch_generic(es.d_plan, es.d_segs + i, es.n_cand[i], ctx->sm_count, es.st));
+                CUDA_TRY(launch_generic(es.d_plan, es.d_segs + i, es.n_cand[i], i, ctx->sm_count, es.st));
                 if (es.n_cand[i]) { ctx->launches++; es.n_launches++; }
+            }
+            for (size_t k = 0; k < es.slots.size(); k++) {  // settle the exact f64 MIN / MAX cells (generic.cu k_edge_fixup)
+                if (!es.slots[k].off_edge || !n_inputs) continue;
+                const int node = es.meta->slot_node[k];
+                const tagg_node& nd = es.meta->nodes[node];
+                CUDA_TRY(launch_edge_fixup(es.d_segs, es.meta->col_slot[node] + (nd.multi ? 1 : 0), nd.op == TAGG_OP_MIN,
+                                           (uint64_t*)(es.arena + es.slots[k].off_acc), es.arena + es.slots[k].off_seen,
+                                           (const uint64_t*)(es.arena + es.slots[k].off_edge), es.slots[k].capacity, ctx->sm_count, es.st));
+                ctx->launches++;
+                es.n_launches++;
             }
         } else {
             es.path_used = mt > 0 ? 4 : 2;
@@ -667,8 +747,11 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         } else {
             CUDA_TRY(cudaMemcpyAsync(&overflow, es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
         }
+        uint32_t bad_ids = 0;
+        if (es.d_bad_ids) CUDA_TRY(cudaMemcpyAsync(&bad_ids, es.d_bad_ids, 4, cudaMemcpyDeviceToHost, es.st));
         CUDA_TRY(cudaStreamSynchronize(es.st));
         lap("synced");
+        if (bad_ids) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id filter docset holds ids that are not strictly ascending or >= max_doc of its segment");
         if (whole) {
             es.host_arena = es.call->pinned + at;
             memcpy(&overflow, es.host_arena + es.off_overflow, 4);
@@ -676,26 +759,76 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         float ms = 0;
         cudaEventElapsedTime(&ms, es.ev0, es.ev1);
         ms_total += ms;
+        bool redo = overflow != 0;
         if (!overflow) {
-            bool redo = false;
             for (int k = 0; k < 4 && !redo; k++)
                 if (es.rank[k].active) {
                     rc = pct_rank_collect(es, k);
                     if (rc < 0) return -rc;
-                    if (rc == 0) redo = true;
+                    if (rc == 0) { redo = true; overflow = 3; }
                 }
+        }
+        if (!redo) {
+            // dense tables merge cell by cell on the device; hashed tables, percentile summaries and exact f64 MIN / MAX
+            // cells (NaN / zero order is per rank) as compact results (below)
+            arena_merge = collective && es.meta->pct_node.empty() && !es.edge_exact;
+            for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
+            if (arena_merge) {
+                rc = comm_merge_arena(es);
+                if (rc) return rc;
+                size_t at2 = (es.call->pinned_used + 63) & ~(size_t)63;
+                if (es.call->pinned && at2 + es.arena_bytes <= es.call->pinned_bytes) {
+                    CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at2, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
+                    CUDA_TRY(cudaStreamSynchronize(es.st));
+                    es.host_arena = es.call->pinned + at2;
+                }
+            }
+            {
+                std::lock_guard<std::mutex> g(ctx->mu);
+                if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
+            }
+            if (!res) res = new tagg_result();
+            res->ctx = ctx;
+            res->meta = plan->meta;
+            rc = read_result(es, res);
+            if (rc) {
+                delete res;
+                return rc;
+            }
+            // a column that spans both zeros: the order of the codes picked -0.0 as the minimum (+0.0 as the maximum); if
+            // the other zero was collected too the reference keeps whichever came FIRST (minmax.rs:99-102) — exact path
+            if (!es.edge_exact && edge_straddle && !collective) {
+                bool ambiguous = false;
+                for (size_t k = 0; k < es.slot_edge.size() && !ambiguous; k++) {
+                    if (es.slot_edge[k] != 1) continue;
+                    const uint64_t amb = es.meta->nodes[es.meta->slot_node[k]].op == TAGG_OP_MIN ? F64_NEG_ZERO_BITS : 0ull;
+                    const auto& R = res->slots[k];
+                    for (size_t i = 0; i < R.values.size() && !ambiguous; i++) ambiguous = R.seen[i] && R.values[i] == amb;
+                }
+                if (ambiguous) {
+                    if (ctx->path == 2) { delete res; return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over both signed zeros runs on the exact (generic) path; path is forced to stream"); }
+                    es.edge_exact = true;
+                    redo = true;
+                    std::lock_guard<std::mutex> g(ctx->mu);
+                    res->meta.reset();
+                    res->pcts.clear();
+                    ctx->result_pool.push_back(res);
+                    res = nullptr;
+                }
+            }
             if (!redo) break;
-            overflow = 3;
         }
         if (overflow == 3) es.no_rank = true;  // the rank bins could not resolve this distribution: exact path
         if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
         if (overflow == 4) return tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
-        if (attempt >= 6) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
+        if (overflow == 5) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");
+        if (attempt >= 7) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
         // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
         if (overflow == 1) es.hash_shift += 2;
         pct_rank_release(es);
         cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
-        cudaFreeAsync(es.d_plan, es.st); es.d_plan = nullptr;
+        if (es.d_plan) cudaFreeAsync(es.d_plan, es.st);
+        es.d_plan = nullptr;
         for (int k = 0; k < 4; k++) {
             if (es.pct_codes[k]) cudaFreeAsync(es.pct_codes[k], es.st);
             if (es.pct_buckets[k]) cudaFreeAsync(es.pct_buckets[k], es.st);
@@ -704,33 +837,6 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         }
     }
 
-    // dense tables merge cell by cell on the device; hashed tables and percentile summaries as compact results (below)
-    bool arena_merge = collective && es.meta->pct_node.empty();
-    for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
-    if (arena_merge) {
-        rc = comm_merge_arena(es);
-        if (rc) return rc;
-        size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
-        if (es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes) {
-            CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
-            CUDA_TRY(cudaStreamSynchronize(es.st));
-            es.host_arena = es.call->pinned + at;
-        }
-    }
-
-    tagg_result* res = nullptr;
-    {
-        std::lock_guard<std::mutex> g(ctx->mu);
-        if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
-    }
-    if (!res) res = new tagg_result();
-    res->ctx = ctx;
-    res->meta = plan->meta;
-    rc = read_result(es, res);
-    if (rc) {
-        delete res;
-        return rc;
-    }
     if (collective && !arena_merge) {
         rc = comm_merge_results(es, res);
         if (rc) {

@@ -41,6 +41,7 @@ struct ScopeLayout {
 };
 struct SlotLayout {
     size_t off_acc = 0, off_seen = 0;
+    size_t off_edge = 0;  // exact f64 MIN / MAX (edge mode): 3 * capacity position cells, 0 = none
     uint64_t capacity = 1;
 };
 
@@ -58,6 +59,7 @@ struct ExecState {
     DevSegment* d_segs = nullptr;
     std::vector<uint64_t> n_cand;    // candidates per segment (ids count or max_doc)
     std::vector<void*> temps;        // device allocations to release at the end
+    uint32_t* d_bad_ids = nullptr;   // set by k_ids_to_bitset when a SORTED_IDS filter docset is malformed
 
     std::vector<ScopeLayout> scopes;
     std::vector<SlotLayout> slots;
@@ -91,6 +93,11 @@ struct ExecState {
         PctSummary summary;          // filled by pct_rank_collect
     } rank[4];
     bool no_rank = false;            // a rank-bin pass failed its precision check: redo on the exact path
+    // f64 MIN / MAX follow the reference's PartialOrd fold (minmax.rs:97-106): per slot, 0 = the order of the codes is
+    // exact, 1 = the column spans both zeros (exact unless the result is the ambiguous zero: checked after the read-out),
+    // 2 = the column holds a NaN.  edge_exact: run the plan on the generic kernel with position tracking (generic.cu)
+    std::vector<uint8_t> slot_edge;
+    bool edge_exact = false;
 
     uint64_t alg_bytes = 0;
     uint64_t direct_bytes = 0;  // host docset bytes the kernels read in place over PCIe

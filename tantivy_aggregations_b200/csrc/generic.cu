@@ -19,7 +19,7 @@ __device__ __forceinline__ bool pred_test(const DevNode& nd, uint64_t code) {
 
 // One value folded into a SUM / MIN / MAX leaf (sum.rs:95-102, minmax.rs:97-106).
 __device__ __forceinline__ void fold_value(const DevPlan* P, const DevNode& nd, uint32_t bucket, uint64_t code,
-                                           uint64_t* racc, uint32_t& rseen) {
+                                           uint64_t* racc, uint32_t& rseen, uint64_t pos) {
     int ri = P->slot_root_index[nd.slot];
     if (ri >= 0) {  // root scope: per-thread accumulator, reduced once at the end of the kernel
         if (nd.op == TAGG_OP_SUM) {
@@ -42,6 +42,20 @@ __device__ __forceinline__ void fold_value(const DevPlan* P, const DevNode& nd, 
             atomicAdd((double*)(sl.acc + bucket), code_to_f64(code));
         else
             atomicAdd((unsigned long long*)(sl.acc + bucket), (unsigned long long)code_to_bits(nd.kind, code));
+    } else if (sl.edge) {
+        // Exact `PartialOrd` fold of minmax.rs:97-106 on f64: a NaN never replaces, but a FIRST NaN sticks; among the two
+        // zeros the first one seen stays.  Record the earliest position of any value / of each zero; NaNs stay out of the
+        // order-preserving min / max; k_edge_fixup settles the cell after the pass.
+        const uint64_t tag = ~pos;
+        if (*((volatile uint64_t*)(sl.edge + bucket)) < tag) atomicMax((unsigned long long*)(sl.edge + bucket), (unsigned long long)tag);
+        if (code == CODE_NEG_ZERO || code == CODE_POS_ZERO) {
+            uint64_t* z = sl.edge + (code == CODE_NEG_ZERO ? 1 : 2) * sl.edge_cap + bucket;
+            if (*((volatile uint64_t*)z) < tag) atomicMax((unsigned long long*)z, (unsigned long long)tag);
+        }
+        if (code >= CODE_NEG_INF && code <= CODE_POS_INF) {
+            uint64_t v = nd.op == TAGG_OP_MIN ? ~code : code;
+            if (*((volatile uint64_t*)(sl.acc + bucket)) < v) atomicMax((unsigned long long*)(sl.acc + bucket), (unsigned long long)v);
+        }
     } else {
         uint64_t v = nd.op == TAGG_OP_MIN ? ~code : code;
         // the plain read may be stale but the cell only grows: skipping when v <= stale is safe
@@ -58,12 +72,17 @@ struct Frame {
 };
 
 __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, const DevSegment* __restrict__ Sp,
-                                                 uint64_t n_cand) {
+                                                 uint64_t n_cand, uint32_t seg_index) {
     const DevSegment& S = *Sp;
     uint64_t racc[TAGG_MAX_ROOT_SLOTS];
     uint32_t rseen = 0;
+    const uint64_t pos_base = (uint64_t)seg_index << EDGE_POS_BITS;
 #pragma unroll
     for (int i = 0; i < TAGG_MAX_ROOT_SLOTS; i++) racc[i] = 0;
+    for (uint32_t ri = 0; ri < P->n_root_slots; ri++) {  // f64 sums fold from -0.0 (x + -0.0 == x, so the first value "replaces")
+        const DevNode& rn = P->nodes[P->root_slot_nodes[ri]];
+        if (rn.op == TAGG_OP_SUM && rn.kind == TAGG_F64) racc[ri] = F64_NEG_ZERO_BITS;
+    }
 
     const uint32_t n_nodes = P->n_nodes;
     const bool by_ids = S.main.kind == DS_IDS;
@@ -72,6 +91,12 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
         uint32_t doc;
         if (by_ids) {
             doc = S.main.ids[i];
+            // the ids come from the caller: one the segment does not have, or a list that is not strictly ascending (what a
+            // tantivy scorer yields), fails the call instead of reading out of bounds / double counting
+            if (doc >= S.max_doc || (i > 0 && S.main.ids[i - 1] >= doc)) {
+                atomicExch(P->overflow, 5u);
+                if (doc >= S.max_doc) continue;
+            }
         } else {
             doc = (uint32_t)i;
             if (!docset_test(S, S.main, doc)) continue;
@@ -121,10 +146,10 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                 case TAGG_OP_MIN:
                 case TAGG_OP_MAX: {
                     if (!nd.multi) {
-                        fold_value(P, nd, bucket, col_get(S.cols[nd.col], doc), racc, rseen);
+                        fold_value(P, nd, bucket, col_get(S.cols[nd.col], doc), racc, rseen, pos_base | doc);
                     } else {  // sum.rs:131-140, minmax.rs:135-145: every value of the doc
                         uint64_t a = col_get(S.cols[nd.col], doc), b = col_get(S.cols[nd.col], (uint64_t)doc + 1);
-                        for (uint64_t j = a; j < b; j++) fold_value(P, nd, bucket, col_get(S.cols[nd.col + 1], j), racc, rseen);
+                        for (uint64_t j = a; j < b; j++) fold_value(P, nd, bucket, col_get(S.cols[nd.col + 1], j), racc, rseen, pos_base | j);
                     }
                     pc++;
                     break;
@@ -237,12 +262,41 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
     }
 }
 
-cudaError_t launch_generic(const DevPlan* dplan, const DevSegment* dseg, uint64_t n_cand, int sm_count,
+cudaError_t launch_generic(const DevPlan* dplan, const DevSegment* dseg, uint64_t n_cand, uint32_t seg_index, int sm_count,
                            cudaStream_t stream) {
     if (n_cand == 0) return cudaSuccess;
     uint64_t blocks = (n_cand + 255) / 256;
     uint64_t cap = (uint64_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
-    k_generic<<<(unsigned)blocks, 256, 0, stream>>>(dplan, dseg, n_cand);
+    k_generic<<<(unsigned)blocks, 256, 0, stream>>>(dplan, dseg, n_cand, seg_index);
+    return cudaGetLastError();
+}
+
+// After the pass, per cell of an f64 MIN / MAX slot in edge mode: the reference's fold returns the FIRST collected value
+// if that value is NaN (nothing is `lt` / `gt` a NaN, minmax.rs:99-102), else the extreme of the non-NaN values, and
+// when that extreme is a zero and both zeros were collected, the zero that came first (-0.0 == +0.0 never replaces).
+__global__ void k_edge_fixup(const DevSegment* __restrict__ segs, int col, int is_min, uint64_t* __restrict__ acc,
+                             const uint8_t* __restrict__ seen, const uint64_t* __restrict__ edge, uint64_t cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t tag = edge[i];
+        if (!tag || !seen[i]) continue;
+        const uint64_t pos = ~tag;
+        const uint64_t first = col_get(segs[pos >> EDGE_POS_BITS].cols[col], pos & ((1ull << EDGE_POS_BITS) - 1));
+        if (first < CODE_NEG_INF || first > CODE_POS_INF) { acc[i] = is_min ? ~first : first; continue; }
+        const uint64_t cur = is_min ? ~acc[i] : acc[i];
+        if (cur == CODE_NEG_ZERO || cur == CODE_POS_ZERO) {
+            const uint64_t nz = edge[cap + i], pz = edge[2 * cap + i];
+            if (nz && pz) {
+                const uint64_t pick = nz > pz ? CODE_NEG_ZERO : CODE_POS_ZERO;  // larger tag = earlier position
+                acc[i] = is_min ? ~pick : pick;
+            }
+        }
+    }
+}
+cudaError_t launch_edge_fixup(const DevSegment* segs, int col, int is_min, uint64_t* acc, const uint8_t* seen, const uint64_t* edge,
+                              uint64_t cap, int sm_count, cudaStream_t stream) {
+    uint64_t blocks = (cap + 255) / 256, lim = (uint64_t)sm_count * 8;
+    if (blocks > lim) blocks = lim;
+    k_edge_fixup<<<(unsigned)blocks, 256, 0, stream>>>(segs, col, is_min, acc, seen, edge, cap);
     return cudaGetLastError();
 }

@@ -117,6 +117,7 @@ struct tagg_plan {
     std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
     // multi-GPU: key domains agreed across ranks, cached per segment set (exec.cu)
     mutable std::mutex mu;
+    mutable bool dom_cache_ok = false;  // tagg_plan_set_collective_cache: the caller vouches for lock-step reuse
     mutable std::vector<const void*> dom_key;
     mutable std::vector<uint64_t> dom_local, dom_agreed;
 };
@@ -142,15 +143,17 @@ struct tagg_result {
 };
 
 // ---- kernels' launchers (generic.cu, stream.cu, columns.cu) ------------------------------------------
-cudaError_t launch_generic(const DevPlan* dplan, const DevSegment* dseg, uint64_t n_cand, int sm_count,
+cudaError_t launch_generic(const DevPlan* dplan, const DevSegment* dseg, uint64_t n_cand, uint32_t seg_index, int sm_count,
                            cudaStream_t stream);
+cudaError_t launch_edge_fixup(const DevSegment* segs, int col, int is_min, uint64_t* acc, const uint8_t* seen, const uint64_t* edge,
+                              uint64_t cap, int sm_count, cudaStream_t stream);
 
 // columns.cu
 int column_from_bytes(tagg_ctx* ctx, int kind, const uint8_t* bytes, size_t len, uint64_t n_values, HostColumn* out);
 int column_from_device_codes(tagg_ctx* ctx, int kind, const uint64_t* d_codes, uint64_t n, HostColumn* out,
                              cudaStream_t stream);
 void column_free(HostColumn* c);
-cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* words, cudaStream_t stream);
+cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* words, uint32_t max_doc, uint32_t* bad, cudaStream_t stream);
 
 // result.cu
 int result_merge(tagg_result* dst, const tagg_result* src);

@@ -41,8 +41,8 @@ enum { MO_SUM = 1, MO_MIN = 2, MO_MAX = 4 };
 // global access per occurrence:
 //   SEEN_BUCKET   single-valued leaf: Some exactly where the bucket exists (aliased to the bucket-existence flags)
 //   SEEN_DERIVED  read off an accumulator after the pass (k_mterms_fixup): a min / max cell that left its identity,
-//                 or an f64 sum cell that left -0.0 (the cells start at -0.0: x + -0.0 == x for every x, and only
-//                 contributions that ARE the identity need an explicit flag store)
+//                 or an f64 sum cell that left -0.0 (every f64 sum cell starts at -0.0: x + -0.0 == x for every x, and
+//                 only contributions that ARE the identity need an explicit flag store)
 //   SEEN_EXPLICIT check-and-set per occurrence (integer sums only: every bit pattern is a legitimate sum)
 enum { SEEN_BUCKET = 0, SEEN_DERIVED = 1, SEEN_EXPLICIT = 2 };
 // bucket existence: from the bucket counts after the pass | CTA bitmap in shared memory flushed at the end |
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                 const ColS& vc = cs[3 + 2 * g];
                 uint64_t sum[MT_DU], mn[MT_DU], mx[MT_DU];  // min in max-form (~code), like the arena
 #pragma unroll
-                for (int u = 0; u < MT_DU; u++) { sum[u] = 0; mn[u] = 0; mx[u] = 0; }
+                for (int u = 0; u < MT_DU; u++) { sum[u] = G.kind == TAGG_F64 ? NEG_ZERO_BITS : 0ull; mn[u] = 0; mx[u] = 0; }  // f64 sums fold from -0.0
                 for (uint64_t r = 0;; r++) {  // round r: the r-th value of each of the thread's documents
                     uint64_t code[MT_DU];
                     bool live[MT_DU], any = false;
@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
 #pragma unroll
                         for (int u = 0; u < MT_U; u++)
                             if (((f[u] >> (1 + g)) & 1u) && !G.seen[b[u]]) G.seen[b[u]] = 1;
-                    } else if (G.seen_mode == SEEN_DERIVED && G.derive_op != MO_SUM) {  // a contribution equal to the identity leaves
-                        // no trace in the cell (a folded f64 sum starts from +0.0 and is never the -0.0 identity)
+                    } else if (G.seen_mode == SEEN_DERIVED) {  // a contribution equal to the identity leaves no trace in the
+                        // cell (min / max: the smallest / largest code; f64 sum: a document whose values are all -0.0)
                         const uint64_t* ss = (const uint64_t*)(base + (G.derive_op == MO_SUM ? G.soff_sum : G.derive_op == MO_MIN ? G.soff_min : G.soff_max));
                         const uint64_t ident = G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull;
 #pragma unroll
@@ -361,12 +361,8 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
     }
 }
 
-// before the pass: f64 sum cells whose Option flags are derived start at -0.0
-__global__ void k_mterms_init(uint64_t* __restrict__ acc, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc[i] = NEG_ZERO_BITS;
-}
-// after the pass: Option flags from the accumulators, untouched -0.0 cells back to the arena's zero identity,
-// bucket existence from the counts
+// after the pass: Option flags from the accumulators (every f64 sum cell of the arena starts at -0.0, exec.cu
+// layout_arena), bucket existence from the counts
 struct MFix {
     uint64_t n;
     uint8_t* present;
@@ -381,7 +377,6 @@ __global__ void k_mterms_fixup(const MFix x) {
             const uint64_t v = x.g[g].cell[i];
             if (x.g[g].derive_op == MO_SUM) {
                 if (v != NEG_ZERO_BITS) x.g[g].seen[i] = 1;
-                else if (!x.g[g].seen[i]) x.g[g].cell[i] = 0;
             } else if (v != 0) {
                 x.g[g].seen[i] = 1;
             }
@@ -571,12 +566,6 @@ int mterms_try(ExecState& es) {
                 if (cudaStreamWaitEvent(es.st, es.call->chunk_ev[c], 0) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "stream ordering failed");
         const uint64_t n_cells = L.capacity;
         const unsigned aux_grid = (unsigned)std::min<uint64_t>((n_cells + 255) / 256, (uint64_t)es.ctx->sm_count * 8);
-        for (int g = 0; g < p.n_groups; g++)
-            if (p.groups[g].seen_mode == SEEN_DERIVED && p.groups[g].derive_op == MO_SUM) {
-                k_mterms_init<<<aux_grid, 256, 0, es.st>>>(p.groups[g].acc_sum, n_cells);
-                es.ctx->launches++;
-                es.n_launches++;
-            }
         {
             // one persistent launch over the tiles of every segment
             const size_t nseg = es.hsegs.size();

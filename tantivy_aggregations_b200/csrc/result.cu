@@ -83,6 +83,7 @@ static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks, uint64_t den
 // bucket; every run of one bucket is an exactly sorted multiset of which a rank schedule is kept (every rank up to 256,
 // then geometric with ratio 1 + eps/4 — the stored neighbour of any target rank is within eps/8 of it)
 static int read_nested_percentiles(ExecState& es, tagg_result* res, size_t k, uint64_t n, const std::vector<uint32_t>& raw_scope) {
+    if (n > 0x7fffffffull) return tagg_fail(TAGG_ERR_UNSUPPORTED, "more than 2^31-1 percentile values in one call (%llu): split the call by segment and merge", (unsigned long long)n);
     uint64_t* d_codes_alt = nullptr;
     uint32_t* d_bkt_alt = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&d_codes_alt, n * 8, es.st)); es.temps.push_back(d_codes_alt);
@@ -176,6 +177,7 @@ static int read_percentiles(ExecState& es, tagg_result* res, const std::vector<s
             continue;
         }
         sum.n_total = n;
+        if (n > 0x7fffffffull) return tagg_fail(TAGG_ERR_UNSUPPORTED, "more than 2^31-1 percentile values in one call (%llu): split the call by segment and merge", (unsigned long long)n);
         if (n) {
             uint64_t* d_alt = nullptr;
             void* d_tmp = nullptr;
@@ -396,10 +398,23 @@ static void merge_pct(PctSummary& a, const PctSummary& b) {
 }
 
 int result_merge(tagg_result* dst, const tagg_result* src) {
-    if (dst->meta.get() != src->meta.get() && dst->meta->nodes.size() != src->meta->nodes.size())
-        return tagg_fail(TAGG_ERR_BAD_ARG, "results come from different plans");
+    if (!dst->meta || !src->meta) return tagg_fail(TAGG_ERR_BAD_ARG, "result has no plan (already freed?)");
+    if (dst->meta.get() != src->meta.get()) {  // different plan objects: the trees must be structurally identical
+        const PlanMeta &a = *dst->meta, &b = *src->meta;
+        bool same = a.nodes.size() == b.nodes.size();
+        for (size_t i = 0; same && i < a.nodes.size(); i++) {
+            const tagg_node &x = a.nodes[i], &y = b.nodes[i];
+            same = x.op == y.op && x.kind == y.kind && x.multi == y.multi && x.field_id == y.field_id && x.n_children == y.n_children &&
+                   memcmp(&x.f0, &y.f0, 8) == 0 && memcmp(&x.f1, &y.f1, 8) == 0 &&
+                   (x.op != TAGG_OP_POST_FILTER || (x.pred == y.pred && x.u0 == y.u0 && x.u1 == y.u1));
+        }
+        if (!same) return tagg_fail(TAGG_ERR_BAD_ARG, "results come from different plans");
+    }
     const PlanMeta& m = *dst->meta;
     size_t ns = m.scope_node.size();
+    if (dst->scopes.size() != ns || src->scopes.size() != ns || dst->slots.size() != m.slot_node.size() || src->slots.size() != m.slot_node.size() ||
+        dst->pcts.size() != m.pct_node.size() || src->pcts.size() != m.pct_node.size())
+        return tagg_fail(TAGG_ERR_BAD_ARG, "result does not have the shape of its plan");
     std::vector<std::vector<uint32_t>> map(ns);  // src bucket -> dst bucket, per scope
     map[0] = {0};
     for (size_t s = 1; s < ns; s++) {

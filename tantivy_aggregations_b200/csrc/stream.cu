@@ -297,6 +297,19 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             const uint32_t nb = BUCKET == BK_HIST ? (uint32_t)p.dom_size : p.side_dom;
             for (uint32_t i = tid; i <= nb; i += blockDim.x) b[i] = p.hist_bounds[i];
         }
+        if (STAB && NBG > 0) {  // f64 sums fold from -0.0 (dev.cuh F64_NEG_ZERO_BITS)
+            bool any = false;
+#pragma unroll
+            for (int g = 0; g < NBG; g++) {
+                const uint32_t ops = (g == 0 && SH::BOPS >= 0) ? (uint32_t)SH::BOPS : p.bgroups[g].ops;
+                if ((ops & OPB_SUM) && p.bgroups[g].kind == TAGG_F64) {
+                    if (!any) __syncthreads();
+                    any = true;
+                    uint64_t* t = (uint64_t*)(smem + p.soff_tab_sum[g]);
+                    for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x) t[i] = F64_NEG_ZERO_BITS;
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         uint64_t rsum[NRG ? NRG : 1], rmin[NRG ? NRG : 1], rmax[NRG ? NRG : 1];
         bool rseen = false;
 #pragma unroll
-        for (int g = 0; g < NRG; g++) { rsum[g] = 0; rmin[g] = 0; rmax[g] = 0; }
+        for (int g = 0; g < NRG; g++) { rsum[g] = p.rgroups[g].kind == TAGG_F64 ? F64_NEG_ZERO_BITS : 0ull; rmin[g] = 0; rmax[g] = 0; }
         // CT root shape (one f64 column, compile-time ops): min / max run on the packed deltas and are folded into
         // the code domain only when the column's min_value changes (segment change); the sum adds delta + constant
         constexpr bool CTROOT = SH::ROPS >= 0 && NRG == 1;
@@ -986,10 +999,8 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 const uint64_t* ss = (const uint64_t*)(smem + p.soff_tab_sum[g]);
                 for (uint64_t i = tid; i < p.dom_size; i += blockDim.x) {
                     uint64_t v = ss[i];
-                    if (v) {
-                        if (G.kind == TAGG_F64) atomicAdd((double*)(G.acc_sum + i), __longlong_as_double((long long)v));
-                        else atomicAdd((unsigned long long*)(G.acc_sum + i), (unsigned long long)v);
-                    }
+                    if (G.kind == TAGG_F64) { if (v != F64_NEG_ZERO_BITS) atomicAdd((double*)(G.acc_sum + i), __longlong_as_double((long long)v)); }
+                    else if (v) atomicAdd((unsigned long long*)(G.acc_sum + i), (unsigned long long)v);
                 }
             }
             if (p.tab_filt) continue;  // filter tables: the exact extremes went to the global table directly

@@ -121,37 +121,82 @@ def f64_bits(x):
     return struct.unpack("<Q", struct.pack("<d", float(x)))[0]
 
 
-def assert_fruit_equal(got, want, f64_sum_rtol=0.0, path="fruit"):
+def assert_fruit_equal(got, want, f64_sum_rtol=0.0, path="fruit", nan_equal=False):
     """Structural equality of two fruits.  Everything is bit-exact except f64 values when
-    f64_sum_rtol > 0 (then |got-want| <= rtol*|want| is accepted, for order-dependent f64 sums)."""
+    f64_sum_rtol > 0 (then |got-want| <= rtol*|want| is accepted, for order-dependent f64 sums; a zero must still
+    match in sign) and, with nan_equal, any two NaNs (an f64 sum that is NaN carries no defined payload)."""
     if isinstance(want, tuple):
         assert isinstance(got, tuple) and len(got) == len(want), f"{path}: tuple arity {got!r} vs {want!r}"
         for i, (g, w) in enumerate(zip(got, want)):
-            assert_fruit_equal(g, w, f64_sum_rtol, f"{path}.{i}")
+            assert_fruit_equal(g, w, f64_sum_rtol, f"{path}.{i}", nan_equal)
     elif isinstance(want, Terms):
         assert isinstance(got, Terms), f"{path}: {type(got)}"
         assert set(got.res) == set(want.res), f"{path}: bucket keys differ: {sorted(set(got.res) ^ set(want.res))[:10]}"
         for k in want.res:
-            assert_fruit_equal(got.res[k], want.res[k], f64_sum_rtol, f"{path}[{k}]")
+            assert_fruit_equal(got.res[k], want.res[k], f64_sum_rtol, f"{path}[{k}]", nan_equal)
     elif isinstance(want, Histogram):
         assert isinstance(got, Histogram), f"{path}: {type(got)}"
         assert f64_bits(got.start) == f64_bits(want.start) and f64_bits(got.interval) == f64_bits(want.interval)
         assert set(got._buckets) == set(want._buckets), f"{path}: bucket ords differ {sorted(got._buckets)} vs {sorted(want._buckets)}"
         for k in want._buckets:
-            assert_fruit_equal(got._buckets[k], want._buckets[k], f64_sum_rtol, f"{path}<{k}>")
-    elif hasattr(want, "percentile") :
+            assert_fruit_equal(got._buckets[k], want._buckets[k], f64_sum_rtol, f"{path}<{k}>", nan_equal)
+    elif hasattr(want, "percentile"):
         assert hasattr(got, "percentile"), f"{path}: {type(got)}"
         assert got.n == want.n, f"{path}: percentile n {got.n} vs {want.n}"
+        assert_percentiles_agree(got, want, path)
     elif isinstance(want, float):
         assert isinstance(got, float), f"{path}: {got!r} vs {want!r}"
         if f64_bits(got) == f64_bits(want):
             return
-        if f64_sum_rtol > 0 and not math.isnan(want):
+        if nan_equal and math.isnan(want) and math.isnan(got):
+            return
+        if f64_sum_rtol > 0 and not math.isnan(want) and want != 0.0:
             assert abs(got - want) <= f64_sum_rtol * abs(want), f"{path}: {got!r} vs {want!r} (rtol {f64_sum_rtol})"
         else:
             raise AssertionError(f"{path}: f64 bits differ: {got!r} vs {want!r}")
     else:
         assert got == want and type(got) == type(want), f"{path}: {got!r} vs {want!r}"
+
+
+PCT_QS = (0.01, 0.25, 0.5, 0.75, 0.95, 0.99)
+
+
+def assert_percentiles_agree(got, want, path="pct", qs=PCT_QS, eps=0.01):
+    """percentile(q) of the product fruit (exact order statistics) against the oracle's CKMS sketch (percentile.rs:163-177).
+
+    * while the sketch holds every value (no compression yet: every g == 1, delta == 0) both answer with the same order
+      statistic, so the values must be EQUAL;
+    * otherwise the sketch only brackets ranks: sample i stands for g_i inserted values in (v_{i-1}, v_i] (compress folds a
+      sample into its right neighbour only), so a value x has more than sum(g_j : v_j < x) values below it and fewer than
+      sum(g_j : j <= first sample above x) at or below it, each good to eps * rank.  The (rank, value) pair the product
+      answers with must sit inside that bracket, and the rank within the estimator's own band eps*k (+1) of the rank k
+      CKMS targets.
+    Skipped when the sketch's weights do not add up to n (the reference's lossy thread-pool merge, percentile.rs:58-62)."""
+    samples = getattr(want, "samples", None)
+    if samples is None or not want.n:
+        for q in qs:
+            assert got.percentile(q) == want.percentile(q), f"{path}: percentile({q})"
+        return
+    if sum(g for _, g, _ in samples) != want.n:
+        return
+    uncompressed = len(samples) == want.n and all(g == 1 and d == 0 for _, g, d in samples)
+    vals = np.array([v for v, _, _ in samples])
+    rmin = np.cumsum([g for _, g, _ in samples])
+    for q in qs:
+        x = got.percentile(q)
+        assert x is not None, f"{path}: percentile({q}) is None"
+        if uncompressed:
+            assert f64_bits(x) == f64_bits(want.percentile(q)), f"{path}: percentile({q}) {x!r} vs {want.percentile(q)!r}"
+            continue
+        k, r = got.rank_of_answer(q)
+        assert abs(r - k) <= eps * k + 1, f"{path}: percentile({q}) answers rank {r}, CKMS targets {k}"
+        below = np.searchsorted(vals, x, side="left")    # samples < x
+        above = np.searchsorted(vals, x, side="right")   # first sample > x
+        # (CKMS's cumulative weights are themselves only good to eps * rank — measured on the restatement — hence the slack)
+        lo = int(rmin[below - 1]) + 1 if below > 0 else 1
+        hi = int(rmin[above]) - 1 if above < len(vals) else want.n
+        lo, hi = lo - (eps * lo + 1), hi + (eps * hi + 1)
+        assert lo <= r <= hi, f"{path}: percentile({q}) = {x!r} claims rank {r}, the oracle sketch brackets it to [{lo}, {hi}]"
 
 
 def exact_rank_window(sorted_vals, value):

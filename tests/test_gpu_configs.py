@@ -1,12 +1,13 @@
 """GPU: BASELINE.json's five configurations at their FULL sizes, checked through size-independent
 properties (conservation of counts, agreement between independent kernels / table implementations,
-rank windows measured on the device) plus a bit-exact oracle comparison on a small extra segment of
-the same synthetic recipe (x(doc) = mix64(seed ^ tag ^ doc * GOLDEN), seed = 1)."""
+rank windows measured on the device), a bit-exact oracle comparison of ONE FULL SEGMENT of C3 / C4 / C5 (C1 and the C2
+bench gate compare everything) and of a small extra segment of the same synthetic recipe
+(x(doc) = mix64(seed ^ tag ^ doc * GOLDEN), seed = 1)."""
 import numpy as np
 import pytest
 
 import tantivy_aggregations_b200 as ta
-from helpers import Corpus, SegSpec, assert_fruit_equal
+from helpers import Corpus, SegSpec, assert_fruit_equal, exact_rank_window
 from tantivy_aggregations_b200 import _ffi as F
 
 pytestmark = pytest.mark.gpu
@@ -122,6 +123,28 @@ def test_c3_histogram_percentiles_500m(ctx):
         k = ta.ckms_target_rank(qq, n_sel)
         band = eps * qq * n_sel + 1
         assert below + 1 - band <= k <= upto + band, (qq, k, below, upto)
+    # ONE FULL SEGMENT (62.5M docs, its own 50 % bitset) against ground truth: the histogram bit for bit against the oracle,
+    # the percentiles against the exactly sorted matched values (the oracle's CKMS needs minutes at this size): every
+    # answer is an element of the input whose exact rank window meets the estimator's band around the rank CKMS targets
+    from oracle import oracle
+    from tantivy_aggregations_b200 import codec
+    per = n // nseg
+    twin = oracle_twin(per, 0, [(F.F64, PRICE, 0, (0, T_PRICE))])
+    sq = ta.BitsetQuery({0: bits[0]})
+    want_hist, _, _ = Corpus([twin]).build_oracle().search(sq, ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()))
+    got_hist, got_pct = ta.Searcher(ctx, [segs[0]]).agg_search(sq, (ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)))
+    assert_fruit_equal(got_hist, want_hist)
+    sel = np.unpackbits(bits[0], bitorder="little")[:per].astype(bool)
+    sv = np.sort(codec.code_to_f64(twin.cols[PRICE][1][sel]))
+    assert got_pct.n == len(sv)
+    for qq in (0.01, 0.25, 0.5, 0.75, 0.95, 0.99):
+        v = got_pct.percentile(qq)
+        lo, hi = exact_rank_window(sv, v)
+        assert hi >= lo, (qq, v, "not an element of the input")
+        k = ta.ckms_target_rank(qq, len(sv))
+        band = eps * qq * len(sv) + 1
+        assert lo - band <= k <= hi + band, (qq, k, lo, hi)
+    del sv, sel, twin
     for s in segs:
         s.close()
     # bit-exact against the oracle on a small twin (same recipe, 300k docs, its own 50 % bitset)
@@ -157,6 +180,13 @@ def test_c4_multivalued_terms_1b_values(ctx):
         d, h = dense.res[k], hashed.res[5 + k * spread]
         assert d[0] == h[0]
         assert (d[1] is None) == (h[1] is None) and (d[1] is None or close(d[1], h[1]))
+    # ONE FULL SEGMENT (15.6M docs, ~62M key occurrences) against the oracle: bucket set and counts bit for bit, f64 sums to 1e-12
+    per = n // nseg
+    twin = oracle_twin(per, 0, [(F.U64, KEYS, 1, (1, T_KEYS, 9, 0, nkeys)), (F.F64, VALS, 1, (0, T_VALS, 3))])
+    full_agg = lambda: ta.terms_agg_u64s(KEYS, (ta.count_agg(), ta.sum_agg_f64s(VALS)))
+    want_full, _, _ = Corpus([twin]).build_oracle().search(ta.AllQuery(), full_agg())
+    assert_fruit_equal(ta.Searcher(ctx, [segs[0]]).agg_search(ta.AllQuery(), full_agg()), want_full, RTOL)
+    del twin, want_full
     for s in segs:
         s.close()
     # bit-exact bucket structure / tolerance sums against the oracle on a small twin
@@ -187,6 +217,15 @@ def test_c5_post_filter_terms_1b(ctx):
     assert close(sum(b[2] for b in terms.res.values()), sm, 1e-10)
     counts = S.agg_search(ta.AllQuery(), pf(ta.terms_agg_u64(CATEGORY, ta.count_agg())))
     assert sum(counts.res.values()) == cnt and set(counts.res) == set(terms.res)
+    # ONE FULL SEGMENT (15.6M docs) against the oracle: buckets, min, max bit for bit, f64 sums to 1e-12
+    per = n // nseg
+    twin = oracle_twin(per, 0, [(F.U64, STATUS, 0, (1, T_STATUS, 0, 4)), (F.U64, CATEGORY, 0, (1, T_CAT, 1, ncat)), (F.F64, PRICE, 0, (0, T_PRICE))])
+    full_agg = lambda: pf(ta.terms_agg_u64(CATEGORY, (ta.min_agg_f64(PRICE), ta.max_agg_f64(PRICE), ta.sum_agg_f64(PRICE))))
+    want_full, _, _ = Corpus([twin]).build_oracle().search(ta.AllQuery(), full_agg())
+    got_full, r1 = ta.Searcher(ctx, [segs[0]]).agg_search_with_executor(ta.AllQuery(), full_agg(), ta.SINGLE_THREAD, return_reader=True)
+    assert r1.stats()["path"] == 2
+    assert_fruit_equal(got_full, want_full, RTOL)
+    del twin, want_full, got_full
     for s in segs:
         s.close()
     m = 250_000
