@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TAGG_ABI_VERSION 1
+#define TAGG_ABI_VERSION 2
 
 typedef enum tagg_status {
     TAGG_OK = 0,
@@ -214,9 +214,18 @@ int tagg_comm_unique_id(uint8_t out[TAGG_UNIQUE_ID_BYTES]);      /* rank 0, then
 int tagg_comm_init(tagg_ctx* ctx, const uint8_t id[TAGG_UNIQUE_ID_BYTES], int rank, int n_ranks);
 int tagg_comm_destroy(tagg_ctx* ctx);
 /* Like tagg_execute over this rank's segments, then one collective merge step;
- * every rank receives the merged fruit.  Collective: all ranks must call it. */
+ * every rank receives the merged fruit.  Collective: all ranks must call it, with plans of the same tree.
+ * Every call agrees the bucket-table layout across ranks with one tiny all-reduce (ranks may change their segment
+ * sets between calls independently); the previous agreement is used optimistically while that all-reduce is in flight. */
 int tagg_execute_collective(const tagg_plan* plan, const tagg_segment_input* inputs,
                             uint32_t n_inputs, tagg_result** out);
+/* The same, but the bucket tables are merged by an NCCL reduce into rank `root` only (the host that answers the query,
+ * searcher.rs:93-96 has ONE harvest): on the root *out is the merged fruit; on the other ranks it is an empty placeholder
+ * (tagg_result_is_local -> 0, every scope / metric length 0).  Plans whose tables cannot be reduced cell by cell (hashed
+ * scopes, percentiles, exact NaN / signed-zero f64 min / max) exchange compact results instead and every rank gets the fruit. */
+int tagg_execute_reduce(const tagg_plan* plan, const tagg_segment_input* inputs,
+                        uint32_t n_inputs, int root, tagg_result** out);
+int tagg_result_is_local(const tagg_result* res, int* out);
 
 /* ---- result readers -----------------------------------------------------------------
  * A plan's bucket scopes are: the root (scope_node = UINT32_MAX, exactly one bucket) and
@@ -235,6 +244,12 @@ int tagg_result_scope_read(const tagg_result* res, uint32_t scope_node,
 int tagg_result_metric_len(const tagg_result* res, uint32_t node, uint64_t* n_buckets);
 int tagg_result_metric_read(const tagg_result* res, uint32_t node,
                             uint64_t* values, uint8_t* seen, uint64_t cap);
+/* Zero-copy views of the same arrays: pointers into the result's (page-locked) image, valid until the result is freed
+ * or merged into.  n = number of buckets. */
+int tagg_result_scope_view(const tagg_result* res, uint32_t scope_node,
+                           const uint64_t** keys, const uint32_t** parents, uint64_t* n);
+int tagg_result_metric_view(const tagg_result* res, uint32_t node,
+                            const uint64_t** values, const uint8_t** seen, uint64_t* n);
 /* PERCENTILES leaf (root scope or nested): an exact rank summary for bucket `bucket`.
  * n_total = values inserted; pairs (ranks[i], value_bits[i]) are exact 1-based order
  * statistics, ascending.  percentile(q) picks the pair nearest the CKMS target rank

@@ -10,6 +10,7 @@
  *   recipe 0 : code(f64 1.0 + 100.0 * ((x >> 11) * 2^-53))   price in [1, 101)
  *   recipe 1 : a + x mod b
  *   recipe 2 : a + (x mod b) * c                              b distinct keys over a wide domain
+ *   recipe 3 : a + floor(b * u^4), u = (x >> 32) * 2^-32      power-law (Zipf-like) keys in [a, a + b), b < 2^32
  * multi-valued: count(doc) = x(doc, tag ^ 0xC0FFEE1234567) mod count_mod,
  *               value j    = recipe(mix64(x(doc, tag) + (j+1) * 0xD6E8FEB86659FD93))
  * The generated codes go through the same device pack path as tagg_column_upload_codes.

@@ -980,6 +980,7 @@ void orc_ckms_free(void* c) { delete (CKMS*)c; }
 //   recipe 0 PRICE : code(f64 1.0 + 100.0 * ((x >> 11) * 2^-53))      (benches/lib.rs:78 shape)
 //   recipe 1 MOD   : a + x mod b                                       (u64 code)
 //   recipe 2 MODSPREAD : a + (x mod b) * c   (b distinct keys spread over a wide domain)
+//   recipe 3 POWERLAW  : a + floor(b * u^4), u = (x >> 32) * 2^-32   (Zipf-like skew: 18 % of the draws hit b/1000 keys)
 uint64_t orc_synth_x(uint64_t seed, uint64_t tag, uint64_t doc) {
     return mix64(seed ^ tag ^ (doc * 0x9E3779B97F4A7C15ull));
 }
@@ -992,6 +993,10 @@ static inline uint64_t synth_value(int recipe, uint64_t x, uint64_t a, uint64_t 
             return f64_to_code(v);
         }
         case 1: return a + x % b;
+        case 3: {
+            const uint64_t u = x >> 32, u2 = (u * u) >> 32, u4 = (u2 * u2) >> 32;
+            return a + ((u4 * (b & 0xffffffffull)) >> 32);
+        }
         default: return a + (x % b) * c;
     }
 }

@@ -92,6 +92,10 @@ SYMBOLS = {
     "tagg_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "tagg_comm_destroy": (C.c_int, [_P]),
     "tagg_execute_collective": (C.c_int, [_P, C.POINTER(SegmentInput), C.c_uint32, _PP]),
+    "tagg_execute_reduce": (C.c_int, [_P, C.POINTER(SegmentInput), C.c_uint32, C.c_int, _PP]),
+    "tagg_result_is_local": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "tagg_result_scope_view": (C.c_int, [_P, C.c_uint32, _PP, _PP, _U64P]),
+    "tagg_result_metric_view": (C.c_int, [_P, C.c_uint32, _PP, _PP, _U64P]),
     "tagg_result_scope_len": (C.c_int, [_P, C.c_uint32, _U64P]),
     "tagg_result_scope_read": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64]),
     "tagg_result_metric_len": (C.c_int, [_P, C.c_uint32, _U64P]),

@@ -345,11 +345,21 @@ int tagg_plan_destroy(tagg_plan* plan) {
 }
 
 int tagg_execute(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_result** out) {
-    return exec_run(plan, inputs, n_inputs, false, out);
+    return exec_run(plan, inputs, n_inputs, 0, -1, out);
 }
 
 int tagg_execute_collective(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_result** out) {
-    return exec_run(plan, inputs, n_inputs, true, out);
+    return exec_run(plan, inputs, n_inputs, 1, -1, out);
+}
+
+int tagg_execute_reduce(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int root, tagg_result** out) {
+    return exec_run(plan, inputs, n_inputs, 2, root, out);
+}
+
+int tagg_result_is_local(const tagg_result* res, int* out) {
+    if (!res || !out) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    *out = res->merged_elsewhere ? 0 : 1;
+    return 0;
 }
 
 int tagg_result_free(tagg_result* res) {
@@ -357,6 +367,7 @@ int tagg_result_free(tagg_result* res) {
         std::lock_guard<std::mutex> live(g_live_mu);
         tagg_ctx* ctx = res->ctx;
         if (g_live_ctx.count(ctx)) {  // (a result may outlive its context)
+            res->release_device();
             res->meta.reset();
             res->pcts.clear();
             std::lock_guard<std::mutex> g(ctx->mu);

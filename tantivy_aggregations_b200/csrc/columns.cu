@@ -83,6 +83,10 @@ __device__ __forceinline__ uint64_t synth_value(int recipe, uint64_t x, uint64_t
         return f64_to_code(v);
     }
     if (recipe == 1) return a + x % b;
+    if (recipe == 3) {  // power-law (Zipf-like) keys: a + floor(b * u^4), u uniform in [0, 1) — integer arithmetic only
+        const uint64_t u = x >> 32, u2 = (u * u) >> 32, u4 = (u2 * u2) >> 32;
+        return a + ((u4 * (b & 0xffffffffull)) >> 32);
+    }
     return a + (x % b) * c;
 }
 __global__ void k_synth(int recipe, uint64_t seed, uint64_t tag, uint64_t doc_base, uint64_t n, uint64_t a,
@@ -377,7 +381,7 @@ int tagg_column_download(const tagg_segment* seg, uint32_t field_id, int which, 
 // ---- synthetic generators ------------------------------------------------------------------------
 int tagg_synth_column(tagg_segment* seg, uint32_t field_id, int kind, int recipe, uint64_t seed, uint64_t tag,
                       uint64_t doc_base, uint64_t a, uint64_t b, uint64_t c) {
-    if (!seg || !valid_kind(kind) || recipe < 0 || recipe > 2 || (recipe && b == 0))
+    if (!seg || !valid_kind(kind) || recipe < 0 || recipe > 3 || (recipe && b == 0))
         return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_synth_column: bad argument");
     tagg_ctx* ctx = seg->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -401,7 +405,7 @@ int tagg_synth_column(tagg_segment* seg, uint32_t field_id, int kind, int recipe
 
 int tagg_synth_multicolumn(tagg_segment* seg, uint32_t field_id, int kind, int recipe, uint64_t seed, uint64_t tag,
                            uint64_t doc_base, uint64_t count_mod, uint64_t a, uint64_t b, uint64_t c) {
-    if (!seg || !valid_kind(kind) || recipe < 0 || recipe > 2 || (recipe && b == 0) || count_mod == 0)
+    if (!seg || !valid_kind(kind) || recipe < 0 || recipe > 3 || (recipe && b == 0) || count_mod == 0)
         return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_synth_multicolumn: bad argument");
     tagg_ctx* ctx = seg->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));

@@ -48,9 +48,18 @@ __global__ void k_reduce_gathered(const uint8_t* __restrict__ gathered, uint8_t*
     }
 }
 
+#define AGREE_MAX (3 * TAGG_MAX_SCOPES + 8)  // words of a key-domain agreement
+
 struct NcclState {
     void* lib = nullptr;
     ncclComm_t comm = nullptr;
+    // key-domain agreement: its own stream, staging in pinned / device memory (one agreement in flight per context)
+    cudaStream_t agree_st = nullptr;
+    cudaEvent_t agree_ev = nullptr;
+    uint64_t* agree_host = nullptr;
+    uint64_t* agree_dev = nullptr;
+    size_t agree_n = 0;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -75,6 +84,7 @@ static int nccl_load(NcclState* s) {
     LOAD(CommInitRank, "ncclCommInitRank")
     LOAD(CommDestroy, "ncclCommDestroy")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(Reduce, "ncclReduce")
     LOAD(AllGather, "ncclAllGather")
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
@@ -119,6 +129,15 @@ int tagg_comm_init(tagg_ctx* ctx, const uint8_t id_bytes[TAGG_UNIQUE_ID_BYTES], 
         delete s;
         return rc;
     }
+    if (cudaStreamCreateWithFlags(&s->agree_st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->agree_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&s->agree_host, AGREE_MAX * 8, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void**)&s->agree_dev, AGREE_MAX * 8) != cudaSuccess) {
+        rc = tagg_fail(TAGG_ERR_CUDA, "communicator staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        s->CommDestroy(s->comm);
+        delete s;
+        return rc;
+    }
     ctx->nccl = s;
     ctx->rank = rank;
     ctx->n_ranks = n_ranks;
@@ -128,6 +147,11 @@ int tagg_comm_init(tagg_ctx* ctx, const uint8_t id_bytes[TAGG_UNIQUE_ID_BYTES], 
 int tagg_comm_destroy(tagg_ctx* ctx) {
     if (!ctx || !ctx->nccl) return 0;
     auto* s = (NcclState*)ctx->nccl;
+    cudaSetDevice(ctx->device);
+    if (s->agree_st) { cudaStreamSynchronize(s->agree_st); cudaStreamDestroy(s->agree_st); }
+    if (s->agree_ev) cudaEventDestroy(s->agree_ev);
+    if (s->agree_host) cudaFreeHost(s->agree_host);
+    if (s->agree_dev) cudaFree(s->agree_dev);
     if (s->comm) s->CommDestroy(s->comm);
     delete s;
     ctx->nccl = nullptr;
@@ -139,25 +163,54 @@ int tagg_comm_destroy(tagg_ctx* ctx) {
 }  // extern "C"
 
 // All ranks must lay their bucket tables out identically: agree on every scope's key domain.
-// in/out: dom[3*s + 0] = smallest key (or ~0 if this rank saw none), [1] = ~largest key, [2] = dense_ok.
-int comm_agree_domains(ExecState& es, std::vector<uint64_t>& dom) {
+// dom[3*s + 0] = smallest key (or ~0 if this rank saw none), [1] = ~largest key, [2] = dense_ok, last word: 0 if this rank
+// needs the exact f64 MIN / MAX path.  One min all-reduce on the communicator's own stream; the call returns at once
+// (the pass can start on the previous agreement meanwhile, exec.cu) and comm_agree_wait delivers the vector.
+int comm_agree_begin(ExecState& es, const std::vector<uint64_t>& dom) {
     auto* s = (NcclState*)es.ctx->nccl;
-    if (!s || dom.empty()) return 0;
-    uint64_t* d = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&d, dom.size() * 8, es.st));
-    CUDA_TRY(cudaMemcpyAsync(d, dom.data(), dom.size() * 8, cudaMemcpyHostToDevice, es.st));
-    NCCL_TRY(s, s->AllReduce(d, d, dom.size(), ncclUint64, ncclMin, s->comm, es.st));
-    CUDA_TRY(cudaMemcpyAsync(dom.data(), d, dom.size() * 8, cudaMemcpyDeviceToHost, es.st));
-    CUDA_TRY(cudaStreamSynchronize(es.st));
-    cudaFreeAsync(d, es.st);
+    if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
+    if (dom.size() > AGREE_MAX) return tagg_fail(TAGG_ERR_BAD_PLAN, "too many bucket scopes for a collective call");
+    s->agree_n = dom.size();
+    if (dom.empty()) return 0;
+    memcpy(s->agree_host, dom.data(), dom.size() * 8);
+    CUDA_TRY(cudaMemcpyAsync(s->agree_dev, s->agree_host, dom.size() * 8, cudaMemcpyHostToDevice, s->agree_st));
+    NCCL_TRY(s, s->AllReduce(s->agree_dev, s->agree_dev, dom.size(), ncclUint64, ncclMin, s->comm, s->agree_st));
+    CUDA_TRY(cudaMemcpyAsync(s->agree_host, s->agree_dev, dom.size() * 8, cudaMemcpyDeviceToHost, s->agree_st));
+    CUDA_TRY(cudaEventRecord(s->agree_ev, s->agree_st));
+    return 0;
+}
+int comm_agree_wait(ExecState& es, std::vector<uint64_t>& agreed) {
+    auto* s = (NcclState*)es.ctx->nccl;
+    if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
+    agreed.assign(s->agree_n, 0);
+    if (!s->agree_n) return 0;
+    CUDA_TRY(cudaEventSynchronize(s->agree_ev));
+    memcpy(agreed.data(), s->agree_host, s->agree_n * 8);
+    // later collectives of this call run on the call's stream: order them behind the agreement explicitly
+    CUDA_TRY(cudaStreamWaitEvent(es.st, s->agree_ev, 0));
     return 0;
 }
 
-int comm_merge_arena(ExecState& es) {
+// In-place merge of the accumulators (dense scopes only: identical layout on every rank).  root < 0: every rank ends up
+// with the merged tables (small arenas: one all-gather + a class-aware reduction in rank order on every rank — one NCCL
+// call, bit-identical f64 sums everywhere; large ones: one all-reduce per reduction class).  root >= 0: ncclReduce per
+// reduction class into `root` only, one group (north_star (6): "bucket tables merged by an NCCL reduce over NVLink").
+int comm_merge_arena(ExecState& es, int root) {
     auto* s = (NcclState*)es.ctx->nccl;
     if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
-    const PlanMeta& m = *es.meta;
-    (void)m;
+    const ncclDataType_t dt[4] = {ncclUint8, ncclUint64, ncclFloat64, ncclUint64};
+    const ncclRedOp_t op[4] = {ncclMax, ncclSum, ncclSum, ncclMax};
+    const size_t esz[4] = {1, 8, 8, 8};
+    if (root >= 0) {
+        NCCL_TRY(s, s->GroupStart());
+        for (int c = 0; c < 4; c++) {
+            size_t bytes = es.cls_end[c] - es.cls_begin[c];
+            if (!bytes) continue;
+            NCCL_TRY(s, s->Reduce(es.arena + es.cls_begin[c], es.arena + es.cls_begin[c], bytes / esz[c], dt[c], op[c], root, s->comm, es.st));
+        }
+        NCCL_TRY(s, s->GroupEnd());
+        return 0;
+    }
     if (es.arena_bytes * (size_t)es.ctx->n_ranks <= (256u << 20)) {
         uint8_t* gathered = nullptr;
         CUDA_TRY(cudaMallocAsync((void**)&gathered, es.arena_bytes * (size_t)es.ctx->n_ranks, es.st));
@@ -173,9 +226,6 @@ int comm_merge_arena(ExecState& es) {
         return 0;
     }
     // the arena is laid out by reduction class (exec.cu layout_arena): one all-reduce per class
-    const ncclDataType_t dt[4] = {ncclUint8, ncclUint64, ncclFloat64, ncclUint64};
-    const ncclRedOp_t op[4] = {ncclMax, ncclSum, ncclSum, ncclMax};
-    const size_t esz[4] = {1, 8, 8, 8};
     NCCL_TRY(s, s->GroupStart());
     for (int c = 0; c < 4; c++) {
         size_t bytes = es.cls_end[c] - es.cls_begin[c];
@@ -183,7 +233,6 @@ int comm_merge_arena(ExecState& es) {
         NCCL_TRY(s, s->AllReduce(es.arena + es.cls_begin[c], es.arena + es.cls_begin[c], bytes / esz[c], dt[c], op[c], s->comm, es.st));
     }
     NCCL_TRY(s, s->GroupEnd());
-    CUDA_TRY(cudaStreamSynchronize(es.st));
     return 0;
 }
 
@@ -250,6 +299,8 @@ int comm_merge_results(ExecState& es, tagg_result* res) {
     auto* s = (NcclState*)es.ctx->nccl;
     if (!s) return tagg_fail(TAGG_ERR_NCCL, "no communicator");
     const int nr = es.ctx->n_ranks;
+    res->materialize();
+    res->merged_elsewhere = 0;
     Writer w;
     serialise(*res, w);
     // sizes, then the padded images

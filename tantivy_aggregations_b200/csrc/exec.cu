@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include <chrono>
+#include <functional>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -26,12 +27,13 @@ ExecState::~ExecState() {
 const void* ExecState::pin(const void* src, size_t bytes) {
     size_t at = (call->pinned_used + 63) & ~(size_t)63;
     if (!call->pinned || at + bytes > call->pinned_bytes) return src;
-    memcpy(call->pinned + at, src, bytes);
+    if (src) memcpy(call->pinned + at, src, bytes);  // (src == nullptr: just a pinned scratch block)
     call->pinned_used = at + bytes;
     return call->pinned + at;
 }
 void ExecState::free_temps() {
     pct_rank_release(*this);
+    compact_release(*this);
     for (void* p : temps) cudaFreeAsync(p, st);
     temps.clear();
     if (arena) cudaFreeAsync(arena, st);
@@ -609,12 +611,16 @@ static int build_dev_plan(ExecState& es) {
     return 0;
 }
 
-int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, bool collective,
+// One call of the hot path.  mode: 0 = this GPU only (tagg_execute), 1 = collective, every rank receives the merged fruit
+// (tagg_execute_collective), 2 = collective, merged on `root` only (tagg_execute_reduce).
+int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int mode, int root,
              tagg_result** out) {
     if (!plan || !out || (n_inputs && !inputs)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_execute: null argument");
     tagg_ctx* ctx = plan->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "tagg_execute_collective needs tagg_comm_init first");
+    const bool collective = mode != 0;
+    if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "collective execution needs tagg_comm_init first");
+    if (mode == 2 && (root < 0 || root >= ctx->n_ranks)) return tagg_fail(TAGG_ERR_BAD_ARG, "root rank %d out of range", root);
 
     static const bool trace = getenv("TAGG_TRACE") != nullptr;
     auto t_begin = std::chrono::steady_clock::now();
@@ -649,8 +655,43 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
     bool edge_straddle = false, edge_nan = false;
     edge_scan(es, &edge_straddle, &edge_nan);
     es.edge_exact = edge_nan;  // a NaN in a column: exact path right away; zeros: only if the result turns out ambiguous
+
+    // Collective: every rank lays its tables out over the SAME key domains, agreed with one tiny min all-reduce per call
+    // (comm.cu).  The agreed vector of the previous call on the same (plan, segment set) is used OPTIMISTICALLY: the pass
+    // starts at once on it while the all-reduce is in flight, and is redone in the rare case the agreement moved (some
+    // rank's segments changed).  Every rank issues exactly one agreement per call, so the NCCL call sequences always match.
+    std::vector<uint64_t> agreed;     // this call's agreement, once it is in
+    bool agree_pending = false;
+    std::vector<uint64_t> dom_used;   // the vector the current pass was laid out with
+
     float ms_total = 0;
     tagg_result* res = nullptr;
+    auto take_result = [&]() {
+        {
+            std::lock_guard<std::mutex> g(ctx->mu);
+            if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
+        }
+        if (!res) res = new tagg_result();
+        res->ctx = ctx;
+        res->meta = plan->meta;
+        res->has_img = false;
+        res->lazy = false;
+        res->merged_elsewhere = 0;
+        res->d_stream = es.st;
+        res->pcts.clear();
+    };
+    auto drop_result = [&]() {
+        if (!res) return;
+        res->release_device();
+        res->meta.reset();
+        res->pcts.clear();
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (ctx->result_pool.size() < 4) ctx->result_pool.push_back(res); else delete res;
+        res = nullptr;
+    };
+    bool ok = false;
+    struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{[&]() { if (!ok) drop_result(); }};
+
     bool arena_merge = false;
     for (int attempt = 0;; attempt++) {
         std::vector<uint64_t> dom, bounds;
@@ -659,22 +700,28 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (collective) {
             // one more agreed word: does ANY rank need the exact f64 MIN / MAX path?  (min-reduced: 0 = yes)
             dom.push_back((edge_straddle || edge_nan) ? 0ull : 1ull);
-            // the agreed domains only depend on the segments' column headers: remember them per segment set
-            std::vector<const void*> key(es.segs.begin(), es.segs.end());
-            std::vector<uint64_t> local = dom;
-            bool hit = false;
-            {
-                std::lock_guard<std::mutex> g(plan->mu);
-                if (plan->dom_cache_ok && plan->dom_key == key && plan->dom_local == local) { dom = plan->dom_agreed; hit = true; }
-            }
-            // The cache is OFF unless the caller vouches that every rank reuses the plan on unchanged segment sets in
-            // lock-step (tagg_plan_set_collective_cache): a rank that hit while another missed would skip a collective
-            if (!hit) {
-                rc = comm_agree_domains(es, dom);
+            if (attempt == 0) {
+                rc = comm_agree_begin(es, dom);
                 if (rc) return rc;
-                std::lock_guard<std::mutex> g(plan->mu);
-                plan->dom_key = key; plan->dom_local = local; plan->dom_agreed = dom;
+                agree_pending = true;
+                std::vector<const void*> key(es.segs.begin(), es.segs.end());
+                bool hit = false;
+                {
+                    std::lock_guard<std::mutex> g(plan->mu);
+                    if (plan->dom_key == key && plan->dom_local == dom && plan->dom_agreed.size() == dom.size()) { dom_used = plan->dom_agreed; hit = true; }
+                }
+                if (!hit) {
+                    rc = comm_agree_wait(es, agreed);
+                    if (rc) return rc;
+                    agree_pending = false;
+                    dom_used = agreed;
+                    std::lock_guard<std::mutex> g(plan->mu);
+                    plan->dom_key = key; plan->dom_local = dom; plan->dom_agreed = agreed;
+                }
+            } else {
+                dom_used = agreed;  // (a redo never issues a second agreement: the other ranks would not)
             }
+            dom = dom_used;
             if (dom.back() == 0) es.edge_exact = true;
             dom.pop_back();
         }
@@ -688,11 +735,11 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         es.skip.assign(es.meta->nodes.size(), 0);
         const bool fast_ok = ctx->path != 1 && !es.edge_exact;
         if (es.edge_exact && ctx->path == 2)
-            return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over NaN or signed zeros runs on the exact (generic) path; path is forced to stream");
+            return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over NaN or signed zeros runs on the exact (generic) path; path is forced to stream");
         int handled = 0;
         if (fast_ok) {
             handled = stream_try(es);
-            if (handled < 0) return -handled;
+            if (handled < 0) return rc = -handled;
         }
         // a rank-bin pass that was planned but whose launch did not happen (its member is not flagged) must not shadow
         // the exact path
@@ -705,12 +752,12 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         int mt = 0;
         if (handled != 1 && fast_ok) {  // K5: terms keyed by multi-valued / hashed fields
             mt = mterms_try(es);
-            if (mt < 0) return -mt;
+            if (mt < 0) return rc = -mt;
             if (mt > 0 && plan_fully_covered(es)) handled = 1;
             else if (mt > 0) handled = 2;
         }
         if (handled != 1) {
-            if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
+            if (ctx->path == 2) return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
             es.path_used = mt > 0 ? 5 : handled == 2 ? 3 : 1;
             rc = alloc_percentile_buffers(es);
             if (rc) return rc;
@@ -737,63 +784,81 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         }
         CUDA_TRY(cudaEventRecord(es.ev1, es.st));
         lap("launched");
-        uint32_t overflow = 0;
-        es.host_arena = nullptr;
-        // small arenas come back whole, in one pinned copy, together with the overflow flag
-        size_t at = (es.call->pinned_used + 63) & ~(size_t)63;
-        bool whole = !collective && es.call->pinned && at + es.arena_bytes <= es.call->pinned_bytes;  // (collective: after the merge)
-        if (whole) {
-            CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(&overflow, es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
+
+        // the optimistic layout: has the agreement confirmed it?
+        if (agree_pending) {
+            rc = comm_agree_wait(es, agreed);
+            if (rc) return rc;
+            agree_pending = false;
+            if (agreed != dom_used) {  // some rank's segments changed: every rank sees the same new vector and redoes the pass
+                {
+                    std::lock_guard<std::mutex> g(plan->mu);
+                    plan->dom_agreed = agreed;
+                }
+                CUDA_TRY(cudaStreamSynchronize(es.st));
+                pct_rank_release(es);
+                cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
+                if (es.d_plan) cudaFreeAsync(es.d_plan, es.st);
+                es.d_plan = nullptr;
+                continue;
+            }
         }
-        uint32_t bad_ids = 0;
-        if (es.d_bad_ids) CUDA_TRY(cudaMemcpyAsync(&bad_ids, es.d_bad_ids, 4, cudaMemcpyDeviceToHost, es.st));
+        // dense tables merge cell by cell on the device, BEFORE the read-out (no host round trip in between: a table that
+        // can be merged this way cannot overflow); hashed tables, percentile summaries and exact f64 MIN / MAX cells (NaN /
+        // zero order is per rank) as compact results, after it
+        arena_merge = collective && es.meta->pct_node.empty() && !es.edge_exact;
+        for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
+        const bool i_read = !(arena_merge && mode == 2 && ctx->rank != root);
+        if (arena_merge) {
+            rc = comm_merge_arena(es, mode == 2 ? root : -1);
+            if (rc) return rc;
+        }
+        uint32_t* flags = (uint32_t*)const_cast<void*>(es.pin(nullptr, 16));  // [overflow][bad ids]
+        uint32_t flags_local[4] = {0, 0, 0, 0};
+        if (!flags) flags = flags_local;
+        flags[0] = flags[1] = 0;
+        take_result();
+        if (i_read) {
+            rc = compact_launch(es);
+            if (rc) return rc;
+            rc = compact_download_begin(es, res);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(&flags[0], es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
+        if (es.d_bad_ids) CUDA_TRY(cudaMemcpyAsync(&flags[1], es.d_bad_ids, 4, cudaMemcpyDeviceToHost, es.st));
         CUDA_TRY(cudaStreamSynchronize(es.st));
         lap("synced");
-        if (bad_ids) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id filter docset holds ids that are not strictly ascending or >= max_doc of its segment");
-        if (whole) {
-            es.host_arena = es.call->pinned + at;
-            memcpy(&overflow, es.host_arena + es.off_overflow, 4);
-        }
+        const uint32_t overflow0 = flags[0];
+        if (flags[1]) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id filter docset holds ids that are not strictly ascending or >= max_doc of its segment");
         float ms = 0;
         cudaEventElapsedTime(&ms, es.ev0, es.ev1);
         ms_total += ms;
+        uint32_t overflow = overflow0;
         bool redo = overflow != 0;
         if (!overflow) {
             for (int k = 0; k < 4 && !redo; k++)
                 if (es.rank[k].active) {
-                    rc = pct_rank_collect(es, k);
-                    if (rc < 0) return -rc;
-                    if (rc == 0) { redo = true; overflow = 3; }
+                    const int pr = pct_rank_collect(es, k);
+                    if (pr < 0) return rc = -pr;
+                    if (pr == 0) { redo = true; overflow = 3; }
                 }
         }
         if (!redo) {
-            // dense tables merge cell by cell on the device; hashed tables, percentile summaries and exact f64 MIN / MAX
-            // cells (NaN / zero order is per rank) as compact results (below)
-            arena_merge = collective && es.meta->pct_node.empty() && !es.edge_exact;
-            for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
-            if (arena_merge) {
-                rc = comm_merge_arena(es);
+            if (i_read) {
+                rc = compact_finish(es, res);
                 if (rc) return rc;
-                size_t at2 = (es.call->pinned_used + 63) & ~(size_t)63;
-                if (es.call->pinned && at2 + es.arena_bytes <= es.call->pinned_bytes) {
-                    CUDA_TRY(cudaMemcpyAsync(es.call->pinned + at2, es.arena, es.arena_bytes, cudaMemcpyDeviceToHost, es.st));
-                    CUDA_TRY(cudaStreamSynchronize(es.st));
-                    es.host_arena = es.call->pinned + at2;
-                }
-            }
-            {
-                std::lock_guard<std::mutex> g(ctx->mu);
-                if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
-            }
-            if (!res) res = new tagg_result();
-            res->ctx = ctx;
-            res->meta = plan->meta;
-            rc = read_result(es, res);
-            if (rc) {
-                delete res;
-                return rc;
+                rc = read_percentiles(es, res);
+                if (rc) return rc;
+            } else {
+                res->merged_elsewhere = 1;
+                res->n_scope.assign(es.scopes.size(), 0);
+                res->off_keys.assign(es.scopes.size(), 0); res->off_parents.assign(es.scopes.size(), 0);
+                res->off_values.assign(es.slots.size(), 0); res->off_seen.assign(es.slots.size(), 0);
+                int r2 = 0;
+                if (!res->img) { res->img = (uint8_t*)malloc(64); res->img_cap = 64; res->img_pinned = false; if (!res->img) r2 = 1; }
+                if (r2) return rc = tagg_fail(TAGG_ERR_OOM, "out of memory");
+                res->has_img = true;
+                res->pcts.resize(es.meta->pct_node.size());
             }
             // a column that spans both zeros: the order of the codes picked -0.0 as the minimum (+0.0 as the maximum); if
             // the other zero was collected too the reference keeps whichever came FIRST (minmax.rs:99-102) — exact path
@@ -802,30 +867,29 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
                 for (size_t k = 0; k < es.slot_edge.size() && !ambiguous; k++) {
                     if (es.slot_edge[k] != 1) continue;
                     const uint64_t amb = es.meta->nodes[es.meta->slot_node[k]].op == TAGG_OP_MIN ? F64_NEG_ZERO_BITS : 0ull;
-                    const auto& R = res->slots[k];
-                    for (size_t i = 0; i < R.values.size() && !ambiguous; i++) ambiguous = R.seen[i] && R.values[i] == amb;
+                    const uint64_t n = res->slot_len(k);
+                    const uint64_t* V = res->slot_values(k);
+                    const uint8_t* Sn = res->slot_seen(k);
+                    for (size_t i = 0; i < n && !ambiguous; i++) ambiguous = Sn[i] && V[i] == amb;
                 }
                 if (ambiguous) {
-                    if (ctx->path == 2) { delete res; return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over both signed zeros runs on the exact (generic) path; path is forced to stream"); }
+                    if (ctx->path == 2) return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over both signed zeros runs on the exact (generic) path; path is forced to stream");
                     es.edge_exact = true;
                     redo = true;
-                    std::lock_guard<std::mutex> g(ctx->mu);
-                    res->meta.reset();
-                    res->pcts.clear();
-                    ctx->result_pool.push_back(res);
-                    res = nullptr;
                 }
             }
             if (!redo) break;
         }
+        drop_result();
         if (overflow == 3) es.no_rank = true;  // the rank bins could not resolve this distribution: exact path
-        if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
-        if (overflow == 4) return tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
-        if (overflow == 5) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");
-        if (attempt >= 7) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
+        if (overflow == 2) return rc = tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
+        if (overflow == 4) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
+        if (overflow == 5) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");
+        if (attempt >= 7) return rc = tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
         // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
         if (overflow == 1) es.hash_shift += 2;
         pct_rank_release(es);
+        compact_release(es);
         cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
         if (es.d_plan) cudaFreeAsync(es.d_plan, es.st);
         es.d_plan = nullptr;
@@ -839,17 +903,14 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
 
     if (collective && !arena_merge) {
         rc = comm_merge_results(es, res);
-        if (rc) {
-            delete res;
-            return rc;
-        }
+        if (rc) return rc;
     }
     lap("read_result");
     res->kernel_ms = ms_total;
     res->alg_bytes = es.alg_bytes;
     res->n_launches = es.n_launches;
     res->path_used = es.path_used;
-    CUDA_TRY(cudaStreamSynchronize(es.st));
     *out = res;
+    ok = true;
     return 0;
 }

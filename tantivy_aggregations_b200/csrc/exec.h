@@ -45,13 +45,22 @@ struct SlotLayout {
     uint64_t capacity = 1;
 };
 
+// compact.cu: the device-side image of the fruit
+struct CompactState {
+    uint8_t* d_img = nullptr;
+    size_t d_bytes = 0;
+    std::vector<uint64_t> cap_scope;
+    std::vector<size_t> d_off_keys, d_off_parents, d_off_values, d_off_seen;
+    std::vector<uint32_t*> d_rank;  // per scope: compact index of every raw cell (only where a child scope / nested percentile needs it)
+    bool one_shot = false, launched = false;
+};
+
 struct ExecState {
     tagg_ctx* ctx = nullptr;
     const tagg_plan* plan = nullptr;
     const PlanMeta* meta = nullptr;
     cudaStream_t st = nullptr;
     CallRes* call = nullptr;
-    const uint8_t* host_arena = nullptr;  // pinned copy of the accumulator arena (small arenas), valid after the sync
     bool collective = false;
 
     std::vector<const tagg_segment*> segs;
@@ -99,6 +108,7 @@ struct ExecState {
     std::vector<uint8_t> slot_edge;
     bool edge_exact = false;
 
+    CompactState compact;
     uint64_t alg_bytes = 0;
     uint64_t direct_bytes = 0;  // host docset bytes the kernels read in place over PCIe
     uint32_t n_launches = 0;
@@ -124,14 +134,22 @@ struct ExecState {
     const void* pin(const void* src, size_t bytes);
 };
 
-int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, bool collective,
+int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int mode, int root,
              tagg_result** out);
-// result.cu: device accumulators -> compact host result
-int read_result(ExecState& es, tagg_result* res);
-// comm.cu: merge the accumulators of all ranks in place (dense scopes), before read_result
-int comm_agree_domains(ExecState& es, std::vector<uint64_t>& dom);
-int comm_merge_arena(ExecState& es);
-// hashed tables / percentile summaries: all-gather the compact results and fold them on the host in rank order
+// compact.cu: device accumulators -> compact image (kernels), its download, the result's directory
+int compact_launch(ExecState& es);
+int compact_download_begin(ExecState& es, tagg_result* res);
+int compact_finish(ExecState& es, tagg_result* res);
+void compact_release(ExecState& es);
+// result.cu: percentile summaries of the exact path (after compact_finish)
+int read_percentiles(ExecState& es, tagg_result* res);
+// comm.cu: the key-domain agreement (one tiny min all-reduce per call, asynchronous: begin, then wait for the vector),
+// the in-place merge of the accumulators of all ranks (dense scopes; root < 0: every rank receives the merged tables,
+// else only `root`), and — for hashed tables / percentile summaries — the all-gather of the compact results folded on
+// the host in rank order
+int comm_agree_begin(ExecState& es, const std::vector<uint64_t>& dom);
+int comm_agree_wait(ExecState& es, std::vector<uint64_t>& agreed);
+int comm_merge_arena(ExecState& es, int root);
 int comm_merge_results(ExecState& es, tagg_result* res);
 // stream.cu: returns 1 if a streaming fast shape handled the plan, 0 if not applicable, <0 = -status
 int stream_try(ExecState& es);

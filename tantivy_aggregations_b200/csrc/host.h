@@ -115,9 +115,9 @@ struct tagg_plan {
     tagg_ctx* ctx = nullptr;
     std::shared_ptr<PlanMeta> meta;
     std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
-    // multi-GPU: key domains agreed across ranks, cached per segment set (exec.cu)
+    // multi-GPU: the key domains agreed across ranks on the previous collective call of this plan; reused optimistically
+    // and re-verified by every call's own agreement (exec.cu)
     mutable std::mutex mu;
-    mutable bool dom_cache_ok = false;  // tagg_plan_set_collective_cache: the caller vouches for lock-step reuse
     mutable std::vector<const void*> dom_key;
     mutable std::vector<uint64_t> dom_local, dom_agreed;
 };
@@ -131,6 +131,23 @@ struct PctSummary {
 struct tagg_result {
     tagg_ctx* ctx = nullptr;
     std::shared_ptr<PlanMeta> meta;
+    // Two representations of the bucket scopes and leaf metrics:
+    //  (a) has_img: the compact image produced on the device (compact.cu), downloaded into `img` (page-locked, recycled
+    //      with the result): [buckets per scope u64][per scope: keys u64, parents u32][per slot: values u64, seen u8] at
+    //      the byte offsets below.  The readers copy straight out of it.
+    //  (b) the vectors: after a host-side merge (PreparedAgg::merge on compact results, result.cu); materialize() moves
+    //      (a) into (b).
+    uint8_t* img = nullptr;
+    size_t img_cap = 0;
+    bool img_pinned = false, has_img = false;
+    std::vector<uint64_t> n_scope;
+    std::vector<size_t> off_keys, off_parents, off_values, off_seen;
+    // the same image in HBM (arrays at capacity stride), kept for top_k / row reads on the device
+    uint8_t* d_img = nullptr;
+    size_t d_bytes = 0;
+    cudaStream_t d_stream = nullptr;
+    std::vector<size_t> d_off_keys, d_off_values, d_off_seen;
+    bool lazy = false;  // arrays were not downloaded (TAGG_READOUT_LAZY): readers fetch on demand
     struct Scope { std::vector<uint64_t> keys; std::vector<uint32_t> parents; };
     struct Slot { std::vector<uint64_t> values; std::vector<uint8_t> seen; };
     std::vector<Scope> scopes;   // by scope id
@@ -140,6 +157,17 @@ struct tagg_result {
     uint64_t alg_bytes = 0;
     uint32_t n_launches = 0;
     uint32_t path_used = 0;
+    uint32_t merged_elsewhere = 0;  // tagg_execute_reduce on a non-root rank: the fruit lives on the root
+
+    uint64_t scope_len(size_t s) const { return has_img ? n_scope[s] : scopes[s].keys.size(); }
+    const uint64_t* scope_keys(size_t s) const { return has_img ? (const uint64_t*)(img + off_keys[s]) : scopes[s].keys.data(); }
+    const uint32_t* scope_parents(size_t s) const { return has_img ? (const uint32_t*)(img + off_parents[s]) : scopes[s].parents.data(); }
+    uint64_t slot_len(size_t k) const { return has_img ? n_scope[meta->scope_of[meta->slot_node[k]]] : slots[k].values.size(); }
+    const uint64_t* slot_values(size_t k) const { return has_img ? (const uint64_t*)(img + off_values[k]) : slots[k].values.data(); }
+    const uint8_t* slot_seen(size_t k) const { return has_img ? img + off_seen[k] : slots[k].seen.data(); }
+    void materialize();     // (a) -> (b)
+    void release_device();  // frees d_img
+    ~tagg_result();
 };
 
 // ---- kernels' launchers (generic.cu, stream.cu, columns.cu) ------------------------------------------

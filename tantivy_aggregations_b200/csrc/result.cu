@@ -13,13 +13,6 @@
 
 #include "exec.h"
 
-#define FULL_COPY_MAX (1ull << 20)  // scopes up to this capacity are copied whole and compacted on the host
-
-template <typename T>
-__global__ void k_gather(const T* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ dst) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        dst[i] = src[idx[i]];
-}
 __global__ void k_gather_ranks(const uint64_t* __restrict__ sorted, const uint64_t* __restrict__ ranks, uint64_t n,
                                uint64_t* __restrict__ dst) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
@@ -30,37 +23,6 @@ static inline uint64_t code_to_bits_h(int kind, uint64_t c) {
     if (kind == TAGG_U64) return c;
     if (kind == TAGG_F64) return (c >> 63) ? (c ^ 0x8000000000000000ull) : ~c;
     return c ^ 0x8000000000000000ull;
-}
-
-// values of `raw` indices out of a device array of `capacity` elements
-template <typename T>
-static int fetch(ExecState& es, const T* d_src, uint64_t capacity, const std::vector<uint32_t>& raw, const uint32_t* d_raw,
-                 std::vector<T>& out) {
-    out.resize(raw.size());
-    if (raw.empty()) return 0;
-    if (es.host_arena) {  // the whole arena is already on the host
-        const T* h = (const T*)(es.host_arena + ((const uint8_t*)d_src - es.arena));
-        if (raw.size() == capacity) memcpy(out.data(), h, capacity * sizeof(T));  // every bucket exists: raw is the identity
-        else for (size_t i = 0; i < raw.size(); i++) out[i] = h[raw[i]];
-        return 0;
-    }
-    if (capacity <= FULL_COPY_MAX) {
-        std::vector<T> full(capacity);
-        CUDA_TRY(cudaMemcpyAsync(full.data(), d_src, capacity * sizeof(T), cudaMemcpyDeviceToHost, es.st));
-        CUDA_TRY(cudaStreamSynchronize(es.st));
-        for (size_t i = 0; i < raw.size(); i++) out[i] = full[raw[i]];
-        return 0;
-    }
-    T* d_dst = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&d_dst, raw.size() * sizeof(T), es.st));
-    unsigned blocks = (unsigned)std::min<uint64_t>((raw.size() + 255) / 256, 4096);
-    k_gather<T><<<blocks, 256, 0, es.st>>>(d_src, d_raw, raw.size(), d_dst);
-    es.ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out.data(), d_dst, raw.size() * sizeof(T), cudaMemcpyDeviceToHost, es.st));
-    CUDA_TRY(cudaStreamSynchronize(es.st));
-    cudaFreeAsync(d_dst, es.st);
-    return 0;
 }
 
 // Ranks kept from an exactly sorted multiset of n values: every rank up to 4096, then a geometric
@@ -82,7 +44,7 @@ static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks, uint64_t den
 // percentiles under a bucket aggregation: the materialised (code, bucket) pairs are sorted by code, then stably by
 // bucket; every run of one bucket is an exactly sorted multiset of which a rank schedule is kept (every rank up to 256,
 // then geometric with ratio 1 + eps/4 — the stored neighbour of any target rank is within eps/8 of it)
-static int read_nested_percentiles(ExecState& es, tagg_result* res, size_t k, uint64_t n, const std::vector<uint32_t>& raw_scope) {
+static int read_nested_percentiles(ExecState& es, tagg_result* res, size_t k, uint64_t n, const std::vector<uint32_t>& rank_of_raw) {
     if (n > 0x7fffffffull) return tagg_fail(TAGG_ERR_UNSUPPORTED, "more than 2^31-1 percentile values in one call (%llu): split the call by segment and merge", (unsigned long long)n);
     uint64_t* d_codes_alt = nullptr;
     uint32_t* d_bkt_alt = nullptr;
@@ -144,16 +106,16 @@ static int read_nested_percentiles(ExecState& es, tagg_result* res, size_t k, ui
             sum.value_bits.push_back(code_to_bits_h(TAGG_F64, vals[i]));
         }
         off += counts[r];
-        // raw bucket index of the enclosing scope -> compact bucket index of the result
-        auto it = std::lower_bound(raw_scope.begin(), raw_scope.end(), uniq[r]);
-        if (it == raw_scope.end() || *it != uniq[r]) return tagg_fail(TAGG_ERR_CUDA, "percentile values in a bucket that does not exist (internal error)");
-        res->pcts[k][(uint64_t)(it - raw_scope.begin())] = std::move(sum);
+        // raw bucket index of the enclosing scope -> compact bucket index of the result (compact.cu rank array)
+        if (uniq[r] >= rank_of_raw.size()) return tagg_fail(TAGG_ERR_CUDA, "percentile values in a bucket that does not exist (internal error)");
+        res->pcts[k][(uint64_t)rank_of_raw[uniq[r]]] = std::move(sum);
     }
     return 0;
 }
 
-static int read_percentiles(ExecState& es, tagg_result* res, const std::vector<std::vector<uint32_t>>& raw) {
+int read_percentiles(ExecState& es, tagg_result* res) {
     const PlanMeta& m = *es.meta;
+    res->pcts.clear();
     res->pcts.resize(m.pct_node.size());
     for (size_t k = 0; k < m.pct_node.size(); k++) {
         if (es.rank[k].active) {  // rank-bin mode: collected (and checked) in exec_run
@@ -171,7 +133,12 @@ static int read_percentiles(ExecState& es, tagg_result* res, const std::vector<s
         if (n > es.pct_cap[k]) n = es.pct_cap[k];
         if (m.scope_of[m.pct_node[k]] != 0) {  // under a bucket aggregation
             if (n) {
-                int rc = read_nested_percentiles(es, res, k, n, raw[m.scope_of[m.pct_node[k]]]);
+                const int sc = m.scope_of[m.pct_node[k]];
+                if ((size_t)sc >= es.compact.d_rank.size() || !es.compact.d_rank[sc]) return tagg_fail(TAGG_ERR_CUDA, "no rank array for scope %d (internal error)", sc);
+                std::vector<uint32_t> rank_of_raw(es.compact.cap_scope[sc]);
+                CUDA_TRY(cudaMemcpyAsync(rank_of_raw.data(), es.compact.d_rank[sc], rank_of_raw.size() * 4, cudaMemcpyDeviceToHost, es.st));
+                CUDA_TRY(cudaStreamSynchronize(es.st));
+                int rc = read_nested_percentiles(es, res, k, n, rank_of_raw);
                 if (rc) return rc;
             }
             continue;
@@ -207,137 +174,36 @@ static int read_percentiles(ExecState& es, tagg_result* res, const std::vector<s
     return 0;
 }
 
-int read_result(ExecState& es, tagg_result* res) {
-    static const bool trace = getenv("TAGG_TRACE") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (trace) fprintf(stderr, "[tagg]   read:%-12s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
-    };
-    const PlanMeta& m = *es.meta;
-    size_t ns = es.scopes.size();
-    // (a recycled result keeps the capacity of its arrays: resize + clear, not assign)
-    res->scopes.resize(ns);
-    for (auto& sc : res->scopes) { sc.keys.clear(); sc.parents.clear(); }
-    res->slots.resize(es.slots.size());
-    for (auto& sl : res->slots) { sl.values.clear(); sl.seen.clear(); }
-    std::vector<std::vector<uint32_t>> raw(ns);   // ascending raw bucket indices that exist
-    std::vector<uint32_t*> d_raw(ns, nullptr);
-
-    raw[0] = {0};
-    res->scopes[0].keys = {0};
-    res->scopes[0].parents = {0};
-    for (size_t s = 1; s < ns; s++) {
-        const ScopeLayout& L = es.scopes[s];
-        const tagg_node& nd = m.nodes[m.scope_node[s]];
-        int ps = m.scope_parent[s];
-        std::vector<uint64_t> keys;
-        std::vector<uint32_t> praw;
-        if (L.mode == SCOPE_DENSE) {
-            std::vector<uint8_t> present_copy;
-            const uint8_t* present = nullptr;
-            if (es.host_arena) {
-                present = es.host_arena + L.off_present;
-            } else {
-                present_copy.resize(L.capacity);
-                CUDA_TRY(cudaMemcpyAsync(present_copy.data(), es.arena + L.off_present, L.capacity, cudaMemcpyDeviceToHost, es.st));
-                CUDA_TRY(cudaStreamSynchronize(es.st));
-                present = present_copy.data();
-            }
-            raw[s].reserve(L.capacity <= (1u << 20) ? (size_t)L.capacity : 4096);
-            if (L.capacity && !memchr(present, 0, L.capacity)) {  // every bucket exists
-                raw[s].resize(L.capacity);
-                for (uint64_t i = 0; i < L.capacity; i++) raw[s][i] = (uint32_t)i;
-            } else {   // 8 flags at a time: most of a big table is empty
-                uint64_t i = 0;
-                for (; i + 8 <= L.capacity; i += 8) {
-                    uint64_t w;
-                    memcpy(&w, present + i, 8);
-                    if (!w) continue;
-                    for (int k = 0; k < 8; k++)
-                        if (present[i + k]) raw[s].push_back((uint32_t)(i + k));
-                }
-                for (; i < L.capacity; i++)
-                    if (present[i]) raw[s].push_back((uint32_t)i);
-            }
-            keys.resize(raw[s].size());
-            praw.resize(raw[s].size());
-            if (L.dom_size == L.capacity) {  // the parent scope has one bucket (the common flat shape)
-                for (size_t i = 0; i < raw[s].size(); i++) { keys[i] = L.dom_min + raw[s][i]; praw[i] = 0; }
-            } else {
-                for (size_t i = 0; i < raw[s].size(); i++) {
-                    keys[i] = L.dom_min + raw[s][i] % L.dom_size;
-                    praw[i] = (uint32_t)(raw[s][i] / L.dom_size);
-                }
-            }
-        } else {
-            std::vector<uint32_t> state_copy;
-            const uint32_t* state = nullptr;
-            if (es.host_arena) {
-                state = (const uint32_t*)(es.host_arena + L.off_state);
-            } else {
-                state_copy.resize(L.capacity);
-                CUDA_TRY(cudaMemcpyAsync(state_copy.data(), es.arena + L.off_state, L.capacity * 4, cudaMemcpyDeviceToHost, es.st));
-                CUDA_TRY(cudaStreamSynchronize(es.st));
-                state = state_copy.data();
-            }
-            for (uint64_t i = 0; i < L.capacity; i++)
-                if (state[i] == ST_READY) raw[s].push_back((uint32_t)i);
-        }
-        if (L.capacity > FULL_COPY_MAX && !raw[s].empty()) {
-            CUDA_TRY(cudaMallocAsync((void**)&d_raw[s], raw[s].size() * 4, es.st));
-            es.temps.push_back(d_raw[s]);
-            CUDA_TRY(cudaMemcpyAsync(d_raw[s], raw[s].data(), raw[s].size() * 4, cudaMemcpyHostToDevice, es.st));
-        }
-        if (L.mode == SCOPE_HASH) {
-            int rc = fetch<uint64_t>(es, (const uint64_t*)(es.arena + L.off_keys), L.capacity, raw[s], d_raw[s], keys);
-            if (rc) return rc;
-            rc = fetch<uint32_t>(es, (const uint32_t*)(es.arena + L.off_parents), L.capacity, raw[s], d_raw[s], praw);
-            if (rc) return rc;
-        }
-        auto& S = res->scopes[s];
-        S.keys.resize(keys.size());
-        S.parents.resize(keys.size());
-        const bool single_parent = raw[ps].size() == 1 && raw[ps][0] == 0;
-        for (size_t i = 0; i < keys.size(); i++) {
-            S.keys[i] = nd.op == TAGG_OP_TERMS ? code_to_bits_h(nd.kind, keys[i]) : keys[i];
-            if (single_parent) {
-                S.parents[i] = 0;
-            } else {
-                auto it = std::lower_bound(raw[ps].begin(), raw[ps].end(), praw[i]);
-                S.parents[i] = (uint32_t)(it - raw[ps].begin());
-            }
-        }
+// ---- the two representations of a result (host.h) ----------------------------------------------------------------
+void tagg_result::materialize() {
+    if (!has_img) return;
+    const size_t ns = n_scope.size(), nk = off_values.size();
+    scopes.resize(ns);
+    slots.resize(nk);
+    for (size_t s = 0; s < ns; s++) {
+        const uint64_t n = n_scope[s];
+        if (s == 0) { scopes[0].keys.assign(1, 0); scopes[0].parents.assign(1, 0); continue; }
+        scopes[s].keys.assign(scope_keys(s), scope_keys(s) + n);
+        scopes[s].parents.assign(scope_parents(s), scope_parents(s) + n);
     }
-    lap("scopes");
-    for (size_t k = 0; k < es.slots.size(); k++) {
-        const SlotLayout& SL = es.slots[k];
-        int node = m.slot_node[k];
-        const tagg_node& nd = m.nodes[node];
-        int s = m.scope_of[node];
-        auto& R = res->slots[k];
-        int rc = fetch<uint64_t>(es, (const uint64_t*)(es.arena + SL.off_acc), SL.capacity, raw[s], d_raw[s], R.values);
-        if (rc) return rc;
-        rc = fetch<uint8_t>(es, es.arena + SL.off_seen, SL.capacity, raw[s], d_raw[s], R.seen);
-        if (rc) return rc;
-        const size_t nv = R.values.size();
-        uint64_t* V = R.values.data();
-        uint8_t* Sn = R.seen.data();
-        const int kind = nd.kind;
-        switch (nd.op) {
-            case TAGG_OP_COUNT: memset(Sn, 1, nv); break;
-            case TAGG_OP_SUM:  // accumulated in the natural type already
-                for (size_t i = 0; i < nv; i++) if (!Sn[i]) V[i] = 0;
-                break;
-            case TAGG_OP_MIN:
-                for (size_t i = 0; i < nv; i++) V[i] = Sn[i] ? code_to_bits_h(kind, ~V[i]) : 0;
-                break;
-            case TAGG_OP_MAX:
-                for (size_t i = 0; i < nv; i++) V[i] = Sn[i] ? code_to_bits_h(kind, V[i]) : 0;
-                break;
-        }
+    for (size_t k = 0; k < nk; k++) {
+        const uint64_t n = slot_len(k);
+        slots[k].values.assign(slot_values(k), slot_values(k) + n);
+        slots[k].seen.assign(slot_seen(k), slot_seen(k) + n);
     }
-    lap("slots");
-    return read_percentiles(es, res, raw);
+    has_img = false;
+    release_device();  // the device image no longer describes this result
+}
+void tagg_result::release_device() {
+    if (!d_img) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (d_stream) cudaFreeAsync(d_img, d_stream); else cudaFree(d_img);
+    d_img = nullptr;
+    d_bytes = 0;
+}
+tagg_result::~tagg_result() {
+    if (d_img) { cudaFree(d_img); d_img = nullptr; }
+    if (img) { if (img_pinned) cudaFreeHost(img); else free(img); img = nullptr; }
 }
 
 // ---- PreparedAgg::merge on compact results --------------------------------------------------------
@@ -412,26 +278,34 @@ int result_merge(tagg_result* dst, const tagg_result* src) {
     }
     const PlanMeta& m = *dst->meta;
     size_t ns = m.scope_node.size();
-    if (dst->scopes.size() != ns || src->scopes.size() != ns || dst->slots.size() != m.slot_node.size() || src->slots.size() != m.slot_node.size() ||
-        dst->pcts.size() != m.pct_node.size() || src->pcts.size() != m.pct_node.size())
-        return tagg_fail(TAGG_ERR_BAD_ARG, "result does not have the shape of its plan");
+    if (dst->merged_elsewhere || src->merged_elsewhere) return tagg_fail(TAGG_ERR_BAD_ARG, "the fruit of a tagg_execute_reduce call lives on the root rank only");
+    dst->materialize();
+    auto shaped = [&](const tagg_result* r) {
+        if (r->pcts.size() != m.pct_node.size()) return false;
+        if (r->has_img) return r->n_scope.size() == ns && r->off_values.size() == m.slot_node.size();
+        return r->scopes.size() == ns && r->slots.size() == m.slot_node.size();
+    };
+    if (!shaped(dst) || !shaped(src)) return tagg_fail(TAGG_ERR_BAD_ARG, "result does not have the shape of its plan");
     std::vector<std::vector<uint32_t>> map(ns);  // src bucket -> dst bucket, per scope
     map[0] = {0};
     for (size_t s = 1; s < ns; s++) {
         auto& D = dst->scopes[s];
-        const auto& S = src->scopes[s];
+        const uint64_t sn = src->scope_len(s);
+        const uint64_t* skeys = src->scope_keys(s);
+        const uint32_t* sparents = src->scope_parents(s);
         int ps = m.scope_parent[s];
         std::unordered_map<std::pair<uint32_t, uint64_t>, uint32_t, PairHash> index;
-        index.reserve(D.keys.size() * 2 + S.keys.size());
+        index.reserve(D.keys.size() * 2 + sn);
         for (size_t i = 0; i < D.keys.size(); i++) index[{D.parents[i], D.keys[i]}] = (uint32_t)i;
-        map[s].resize(S.keys.size());
-        for (size_t i = 0; i < S.keys.size(); i++) {
-            uint32_t dp = map[ps][S.parents[i]];
-            auto key = std::make_pair(dp, S.keys[i]);
+        map[s].resize(sn);
+        for (size_t i = 0; i < sn; i++) {
+            if (sparents[i] >= map[ps].size()) return tagg_fail(TAGG_ERR_BAD_ARG, "malformed result: parent bucket out of range");
+            uint32_t dp = map[ps][sparents[i]];
+            auto key = std::make_pair(dp, skeys[i]);
             auto it = index.find(key);
             if (it == index.end()) {  // or_insert_with(create_fruit)
                 uint32_t at = (uint32_t)D.keys.size();
-                D.keys.push_back(S.keys[i]);
+                D.keys.push_back(skeys[i]);
                 D.parents.push_back(dp);
                 index[key] = at;
                 map[s][i] = at;
@@ -445,16 +319,19 @@ int result_merge(tagg_result* dst, const tagg_result* src) {
         const tagg_node& nd = m.nodes[node];
         int s = m.scope_of[node];
         auto& D = dst->slots[k];
-        const auto& S = src->slots[k];
+        const uint64_t sn = src->slot_len(k);
+        const uint64_t* svalues = src->slot_values(k);
+        const uint8_t* sseen = src->slot_seen(k);
+        if (sn != map[s].size()) return tagg_fail(TAGG_ERR_BAD_ARG, "malformed result: metric length differs from its scope");
         size_t nb = dst->scopes[s].keys.size();
         D.values.resize(nb, 0);
         D.seen.resize(nb, nd.op == TAGG_OP_COUNT ? 1 : 0);
-        for (size_t i = 0; i < S.values.size(); i++) {
+        for (size_t i = 0; i < sn; i++) {
             uint32_t d = map[s][i];
-            if (nd.op == TAGG_OP_COUNT) { D.values[d] += S.values[i]; D.seen[d] = 1; continue; }
-            if (!S.seen[i]) continue;  // None => return
-            if (!D.seen[d]) { D.values[d] = S.values[i]; D.seen[d] = 1; continue; }  // acc.replace(v)
-            uint64_t v = S.values[i], &acc = D.values[d];
+            if (nd.op == TAGG_OP_COUNT) { D.values[d] += svalues[i]; D.seen[d] = 1; continue; }
+            if (!sseen[i]) continue;  // None => return
+            if (!D.seen[d]) { D.values[d] = svalues[i]; D.seen[d] = 1; continue; }  // acc.replace(v)
+            uint64_t v = svalues[i], &acc = D.values[d];
             if (nd.op == TAGG_OP_SUM) acc = nd.kind == TAGG_F64 ? f64_bits(bits_f64(acc) + bits_f64(v)) : acc + v;
             else if (nd.op == TAGG_OP_MIN) { if (lt_bits(nd.kind, v, acc)) acc = v; }
             else { if (lt_bits(nd.kind, acc, v)) acc = v; }
@@ -483,7 +360,7 @@ int tagg_result_scope_len(const tagg_result* res, uint32_t scope_node, uint64_t*
     if (!res || !n_buckets) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     int s = scope_index(res, scope_node);
     if (s < 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
-    *n_buckets = res->scopes[s].keys.size();
+    *n_buckets = res->scope_len(s);
     return 0;
 }
 
@@ -491,10 +368,11 @@ int tagg_result_scope_read(const tagg_result* res, uint32_t scope_node, uint64_t
     if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     int s = scope_index(res, scope_node);
     if (s < 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
-    const auto& S = res->scopes[s];
-    if (cap < S.keys.size()) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
-    if (keys && !S.keys.empty()) memcpy(keys, S.keys.data(), S.keys.size() * 8);
-    if (parents && !S.parents.empty()) memcpy(parents, S.parents.data(), S.parents.size() * 4);
+    const uint64_t n = res->scope_len(s);
+    if (cap < n) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
+    if (s == 0) { if (keys) keys[0] = 0; if (parents) parents[0] = 0; return 0; }
+    if (keys && n) memcpy(keys, res->scope_keys(s), n * 8);
+    if (parents && n) memcpy(parents, res->scope_parents(s), n * 4);
     return 0;
 }
 
@@ -502,7 +380,7 @@ int tagg_result_metric_len(const tagg_result* res, uint32_t node, uint64_t* n_bu
     if (!res || !n_buckets) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
         return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
-    *n_buckets = res->slots[res->meta->slot_of[node]].values.size();
+    *n_buckets = res->slot_len(res->meta->slot_of[node]);
     return 0;
 }
 
@@ -510,10 +388,32 @@ int tagg_result_metric_read(const tagg_result* res, uint32_t node, uint64_t* val
     if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
         return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
-    const auto& S = res->slots[res->meta->slot_of[node]];
-    if (cap < S.values.size()) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
-    if (values && !S.values.empty()) memcpy(values, S.values.data(), S.values.size() * 8);
-    if (seen && !S.seen.empty()) memcpy(seen, S.seen.data(), S.seen.size());
+    const size_t k = res->meta->slot_of[node];
+    const uint64_t n = res->slot_len(k);
+    if (cap < n) return tagg_fail(TAGG_ERR_BAD_ARG, "buffer too small");
+    if (values && n) memcpy(values, res->slot_values(k), n * 8);
+    if (seen && n) memcpy(seen, res->slot_seen(k), n);
+    return 0;
+}
+
+int tagg_result_scope_view(const tagg_result* res, uint32_t scope_node, const uint64_t** keys, const uint32_t** parents, uint64_t* n) {
+    if (!res || !n) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    int s = scope_index(res, scope_node);
+    if (s <= 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
+    *n = res->scope_len(s);
+    if (keys) *keys = *n ? res->scope_keys(s) : nullptr;
+    if (parents) *parents = *n ? res->scope_parents(s) : nullptr;
+    return 0;
+}
+
+int tagg_result_metric_view(const tagg_result* res, uint32_t node, const uint64_t** values, const uint8_t** seen, uint64_t* n) {
+    if (!res || !n) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
+        return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
+    const size_t k = res->meta->slot_of[node];
+    *n = res->slot_len(k);
+    if (values) *values = *n ? res->slot_values(k) : nullptr;
+    if (seen) *seen = *n ? res->slot_seen(k) : nullptr;
     return 0;
 }
 

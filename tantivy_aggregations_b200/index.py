@@ -362,6 +362,30 @@ class ResultReader:
             self._scopes[node] = (keys, parents)
         return self._scopes[node]
 
+    @staticmethod
+    def _view(ptr, n, dtype):
+        if not n or not ptr:
+            return np.zeros(0, dtype=dtype)
+        ctype = {np.uint64: C.c_uint64, np.uint32: C.c_uint32, np.uint8: C.c_uint8}[dtype]
+        return np.ctypeslib.as_array((ctype * n).from_address(ptr))
+
+    def scope_view(self, node):
+        """(keys, parents) as zero-copy numpy views of the result's page-locked image (valid while the reader lives)."""
+        k, p, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        F.check(F.lib().tagg_result_scope_view(self._h, node, C.byref(k), C.byref(p), C.byref(n)))
+        return self._view(k.value, n.value, np.uint64), self._view(p.value, n.value, np.uint32)
+
+    def metric_view(self, node):
+        v, s, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        F.check(F.lib().tagg_result_metric_view(self._h, node, C.byref(v), C.byref(s), C.byref(n)))
+        return self._view(v.value, n.value, np.uint64), self._view(s.value, n.value, np.uint8)
+
+    def is_local(self):
+        """False on the non-root ranks of a tagg_execute_reduce call: the fruit lives on the root."""
+        out = C.c_int()
+        F.check(F.lib().tagg_result_is_local(self._h, C.byref(out)))
+        return bool(out.value)
+
     def scope_children(self, node, parent_bucket):
         """(keys, bucket indices) of the buckets of scope `node` whose parent bucket is `parent_bucket`."""
         if node not in self._children:
@@ -504,16 +528,23 @@ class Searcher:
         """src/searcher.rs:13-17 — default executor is SingleThread."""
         return self.agg_search_with_executor(query, agg, SINGLE_THREAD)
 
-    def agg_search_with_executor(self, query, agg, executor, collective=False, return_reader=False):
+    def agg_search_with_executor(self, query, agg, executor, collective=False, return_reader=False, root=None):
+        """collective=True: every rank folds its own segments, one NCCL merge step, every rank returns the merged fruit;
+        with root=r only rank r does (tagg_execute_reduce) and the other ranks return None."""
         plan = agg if isinstance(agg, Plan) else self.prepare(agg)
         lib = F.lib()
-        run = lib.tagg_execute_collective if collective else lib.tagg_execute
+        if collective and root is not None:
+            run = lambda p, a, n, out: lib.tagg_execute_reduce(p, a, n, int(root), out)
+        else:
+            run = lib.tagg_execute_collective if collective else lib.tagg_execute
         if executor == SINGLE_THREAD:
             # one harvest threaded through every segment (searcher.rs:66-78)
             arr, keep = build_inputs(plan, query, self.segments)
             h = C.c_void_p()
             F.check(run(plan._h, arr, len(self.segments), C.byref(h)))
             reader = ResultReader(h)
+            if not reader.is_local():
+                return (None, reader) if return_reader else None
         else:
             # a fruit per segment, merged in segment order (searcher.rs:79-98)
             if collective:

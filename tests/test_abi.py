@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = F.lib()
-    assert lib.tagg_abi_version() == 1
+    assert lib.tagg_abi_version() == 2
     # struct layouts mirrored in ctypes must match the C header (x86-64 SysV)
     assert C.sizeof(F.Node) == 48
     assert C.sizeof(F.Docset) == 40

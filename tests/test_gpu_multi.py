@@ -43,8 +43,54 @@ def _worker(rank, world, port, out_dir):
             ctx.set_path(path)
             got = local.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, collective=True)
             assert_fruit_equal(got, want, 1e-12, f"{name}/path{path}/rank{rank}")
-    # hashed bucket tables and percentile summaries: merged as compact results (all-gather + PreparedAgg::merge in rank order)
+    # tagg_execute_reduce: ncclReduce of the bucket tables into ONE root; the other ranks get a placeholder
+    for root in range(world):
+        for name, mk in shapes.items():
+            want, _, _ = ox.search(ta.AllQuery(), mk(), mode=1, threads=2)
+            got = local.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, collective=True, root=root)
+            if rank == root:
+                assert_fruit_equal(got, want, 1e-12, f"reduce/{name}/root{root}")
+            else:
+                assert got is None or name in ("multi",), (name, rank, root)  # (a plan that exchanges compact results returns the fruit everywhere)
+    # ONE rank's segment set changes between two calls on the SAME plan (an index refresh on that rank only): every call
+    # re-agrees the table layout, the unchanged ranks notice that their cached agreement moved and redo the pass
+    for name in ("terms", "bench_shape", "nested_dense"):
+        plan = local.prepare(shapes[name]())
+        for drop in (0, 1, 0, 2):
+            mine = list(parts[rank])
+            if rank == world - 1 and drop:
+                mine = mine[:-drop] if drop < len(mine) else []
+            sub = ta.Searcher(ctx, [local.segments[parts[rank].index(i)] for i in mine])
+            kept = sorted(i for r in range(world) for i in (parts[r] if r != world - 1 or not drop else (parts[r][:-drop] if drop < len(parts[r]) else [])))
+            want, _, _ = ox.search(ta.AllQuery(), shapes[name](), mode=1, threads=2, segments=kept)
+            got = sub.agg_search_with_executor(ta.AllQuery(), plan, ta.SINGLE_THREAD, collective=True)
+            assert_fruit_equal(got, want, 1e-12, f"refresh/{name}/drop{drop}/rank{rank}")
+            got = sub.agg_search_with_executor(ta.AllQuery(), plan, ta.SINGLE_THREAD, collective=True, root=0)
+            if rank == 0:
+                assert_fruit_equal(got, want, 1e-12, f"refresh-reduce/{name}/drop{drop}")
+        for i, sgm in enumerate(local.segments):
+            sgm.ord = i
+    # f64 min / max over NaN and signed zeros: per-rank exact fold, merged in rank order (PreparedAgg::merge, minmax.rs:59-72)
     import numpy as np
+    from helpers import SegSpec
+    from tantivy_aggregations_b200 import _ffi as F
+    nan = float("nan")
+    edge_vals = [[3.0, -0.0, 1.0], [nan, 0.0, 2.0], [0.0, -0.0], [nan]]
+    edge_segs = []
+    for v in edge_vals:
+        sp = SegSpec(len(v))
+        sp.col(2, F.F64, np.array(v))
+        sp.col(1, F.U64, np.arange(len(v), dtype=np.uint64) % 2)
+        edge_segs.append(sp)
+    eparts = [[0, 1], [2, 3]] if world == 2 else ta.assign_segments([len(v) for v in edge_vals], world)
+    elocal = Corpus([edge_segs[i] for i in eparts[rank]]).build_gpu(ctx)
+    emk = lambda: (ta.min_agg_f64(2), ta.max_agg_f64(2), ta.terms_agg_u64(1, (ta.min_agg_f64(2), ta.max_agg_f64(2))))
+    # the reference shape of "one fruit per unit, merged in order" with the ranks as units
+    per_rank = [Corpus([edge_segs[i] for i in eparts[r]]).build_oracle().search(ta.AllQuery(), emk())[0] for r in range(world)]
+    want = ta.merge_fruits(emk(), per_rank)
+    got = elocal.agg_search_with_executor(ta.AllQuery(), emk(), ta.SINGLE_THREAD, collective=True)
+    assert_fruit_equal(got, want, 0.0, f"edge/rank{rank}")
+    # hashed bucket tables and percentile summaries: merged as compact results (all-gather + PreparedAgg::merge in rank order)
     from helpers import exact_rank_window
     ctx.set_path(0)
     sparse_key = lambda: ta.terms_agg_u64(5, (ta.count_agg(), ta.min_agg_f64(2)))
