@@ -9,14 +9,15 @@ mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -Iinclude"
 pids=()
-for f in api exec generic stream mterms pct columns result compact comm docset; do
+SRCS="api exec generic stream stream_inst_rt_a stream_inst_rt_b stream_inst_ct_terms stream_inst_ct_hist stream_inst_ct_root mterms pct columns result compact comm docset"
+for f in $SRCS; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$SRC/$f.cu" -nt "$OBJ/$f.o" ] || [ -n "$(find $SRC include -name '*.h' -newer "$OBJ/$f.o" -o -name '*.cuh' -newer "$OBJ/$f.o" | head -1)" ]; then
     ( $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$SRC/$f.cu" -o "$OBJ/$f.o" ) &
     pids+=($!)
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $OBJ/api.o $OBJ/exec.o $OBJ/generic.o $OBJ/stream.o $OBJ/mterms.o $OBJ/pct.o $OBJ/columns.o $OBJ/result.o $OBJ/compact.o $OBJ/comm.o $OBJ/docset.o -lcudart -ldl
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $(for f in $SRCS; do echo $OBJ/$f.o; done) -lcudart -ldl
 make -s -C oracle
 echo "built $OUT"
 # typed C++ host facade: compile its test driver (host-only code over the C ABI)
