@@ -9,7 +9,7 @@ mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -Iinclude"
 pids=()
-SRCS="api exec generic stream stream_inst_rt_a stream_inst_rt_b stream_inst_ct_terms stream_inst_ct_hist stream_inst_ct_root mterms pct columns result compact comm docset"
+SRCS="api exec generic stream stream_inst_rt_a stream_inst_rt_b stream_inst_ct_terms stream_inst_ct_hist stream_inst_ct_root mterms pct columns result compact topk comm docset"
 for f in $SRCS; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$SRC/$f.cu" -nt "$OBJ/$f.o" ] || [ -n "$(find $SRC include -name '*.h' -newer "$OBJ/$f.o" -o -name '*.cuh' -newer "$OBJ/$f.o" | head -1)" ]; then
     ( $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$SRC/$f.cu" -o "$OBJ/$f.o" ) &

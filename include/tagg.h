@@ -196,6 +196,11 @@ int tagg_docset_to_bitset(const tagg_segment* seg, const tagg_docset* in, uint8_
 int tagg_plan_create(tagg_ctx* ctx, const tagg_node* nodes, uint32_t n_nodes,
                      const tagg_blob* blobs, uint32_t n_blobs, tagg_plan** out);
 int tagg_plan_destroy(tagg_plan* plan);
+/* How a result of this plan is read out.  EAGER (default): the compact fruit image is downloaded with the execute call.
+ * LAZY: only the bucket counts are; the image stays in HBM and tagg_result_top_k / tagg_result_*_rows fetch just the rows
+ * they need (the plain readers still work: the first one downloads everything). */
+typedef enum tagg_readout { TAGG_READOUT_EAGER = 0, TAGG_READOUT_LAZY = 1 } tagg_readout;
+int tagg_plan_set_readout(tagg_plan* plan, int readout);
 
 /* ---- execution (replaces collect_segment, searcher.rs:27-51) ------------------------
  * All inputs are folded into ONE fruit, like Executor::SingleThread threading one
@@ -250,6 +255,18 @@ int tagg_result_scope_view(const tagg_result* res, uint32_t scope_node,
                            const uint64_t** keys, const uint32_t** parents, uint64_t* n);
 int tagg_result_metric_view(const tagg_result* res, uint32_t node,
                             const uint64_t** values, const uint8_t** seen, uint64_t* n);
+/* Terms::top_k(k, |bucket| <leaf metric by_node>) (terms.rs:425-457) on the device-resident image: the (at most) k buckets
+ * of the TERMS scope `scope_node` under parent bucket `parent_bucket` (0 for a top-level terms_agg) with the largest value
+ * of the leaf `by_node`, descending; equal values ascending by key (the reference's heap order).  Option metrics order as
+ * Rust's Option (None below every Some); f64 by the total order of the codes.  out_buckets: bucket indices in the order of
+ * tagg_result_scope_read; *n_out of them are written.  A radix select on the GPU when the image is there, else on the host. */
+int tagg_result_top_k(tagg_result* res, uint32_t scope_node, uint64_t parent_bucket, uint32_t by_node, uint64_t k,
+                      uint32_t* out_buckets, uint64_t* n_out);
+/* Rows by bucket index (e.g. the winners of tagg_result_top_k): gathered on the device for a lazily read result. */
+int tagg_result_scope_rows(tagg_result* res, uint32_t scope_node, const uint32_t* buckets, uint64_t n,
+                           uint64_t* keys, uint32_t* parents);
+int tagg_result_metric_rows(tagg_result* res, uint32_t node, const uint32_t* buckets, uint64_t n,
+                            uint64_t* values, uint8_t* seen);
 /* PERCENTILES leaf (root scope or nested): an exact rank summary for bucket `bucket`.
  * n_total = values inserted; pairs (ranks[i], value_bits[i]) are exact 1-based order
  * statistics, ascending.  percentile(q) picks the pair nearest the CKMS target rank

@@ -19,6 +19,7 @@ DOCSET_ALL, DOCSET_BITSET, DOCSET_SORTED_IDS, DOCSET_COLUMN_RANGE, DOCSET_DEVICE
 ROOT_SCOPE = 0xFFFFFFFF
 UNIQUE_ID_BYTES = 128
 PATH_AUTO, PATH_GENERIC, PATH_STREAM = 0, 1, 2
+READOUT_EAGER, READOUT_LAZY = 0, 1
 
 
 class Node(C.Structure):
@@ -96,6 +97,10 @@ SYMBOLS = {
     "tagg_result_is_local": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "tagg_result_scope_view": (C.c_int, [_P, C.c_uint32, _PP, _PP, _U64P]),
     "tagg_result_metric_view": (C.c_int, [_P, C.c_uint32, _PP, _PP, _U64P]),
+    "tagg_plan_set_readout": (C.c_int, [_P, C.c_int]),
+    "tagg_result_top_k": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, _P, _U64P]),
+    "tagg_result_scope_rows": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, _P]),
+    "tagg_result_metric_rows": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, _P, _P]),
     "tagg_result_scope_len": (C.c_int, [_P, C.c_uint32, _U64P]),
     "tagg_result_scope_read": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64]),
     "tagg_result_metric_len": (C.c_int, [_P, C.c_uint32, _U64P]),

@@ -336,6 +336,12 @@ int tagg_plan_create(tagg_ctx* ctx, const tagg_node* nodes, uint32_t n_nodes, co
     return 0;
 }
 
+int tagg_plan_set_readout(tagg_plan* plan, int readout) {
+    if (!plan || (readout != TAGG_READOUT_EAGER && readout != TAGG_READOUT_LAZY)) return tagg_fail(TAGG_ERR_BAD_ARG, "bad readout mode");
+    plan->readout = readout;
+    return 0;
+}
+
 int tagg_plan_destroy(tagg_plan* plan) {
     if (!plan) return 0;
     cudaSetDevice(plan->ctx->device);

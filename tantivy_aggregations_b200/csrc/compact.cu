@@ -274,7 +274,8 @@ static int result_reserve(tagg_result* res, size_t bytes) {
 int compact_download_begin(ExecState& es, tagg_result* res) {
     CompactState& C = es.compact;
     const size_t ns = es.scopes.size();
-    C.one_shot = C.d_bytes <= ((size_t)8 << 20);
+    C.lazy = es.plan->readout == TAGG_READOUT_LAZY;
+    C.one_shot = !C.lazy && C.d_bytes <= ((size_t)8 << 20);
     const size_t bytes = C.one_shot ? C.d_bytes : al64(ns * 8);
     int rc = result_reserve(res, bytes);
     if (rc) return rc;
@@ -284,7 +285,6 @@ int compact_download_begin(ExecState& es, tagg_result* res) {
 
 // After the sync: exact-size copies when the image was too large for one shot, then the result's directory.
 int compact_finish(ExecState& es, tagg_result* res) {
-    const PlanMeta& m = *es.meta;
     CompactState& C = es.compact;
     const size_t ns = es.scopes.size(), nk = es.slots.size();
     res->n_scope.assign(ns, 0);
@@ -294,10 +294,45 @@ int compact_finish(ExecState& es, tagg_result* res) {
     res->off_values.assign(nk, 0); res->off_seen.assign(nk, 0);
     for (size_t s = 1; s < ns; s++)
         if (res->n_scope[s] > C.cap_scope[s]) return tagg_fail(TAGG_ERR_CUDA, "compaction produced more buckets than cells (internal error)");
+    // the device image moves into the result: top_k / row reads run on it (released with the result)
+    res->release_device();
+    res->d_img = C.d_img;
+    res->d_bytes = C.d_bytes;
+    res->d_off_keys = C.d_off_keys;
+    res->d_off_parents = C.d_off_parents;
+    res->d_off_values = C.d_off_values;
+    res->d_off_seen = C.d_off_seen;
+    C.d_img = nullptr;
+    res->has_img = true;
+    res->lazy = false;
+    for (auto& sc : res->scopes) { sc.keys.clear(); sc.parents.clear(); }
+    for (auto& sl : res->slots) { sl.values.clear(); sl.seen.clear(); }
+    if (C.lazy) {  // only the bucket counts came down; the arrays follow on demand (result_ensure_host / row reads)
+        res->lazy = true;
+        return 0;
+    }
     if (C.one_shot) {
         res->off_keys = C.d_off_keys; res->off_parents = C.d_off_parents;
         res->off_values = C.d_off_values; res->off_seen = C.d_off_seen;
-    } else {
+        return 0;
+    }
+    res->lazy = true;
+    return result_ensure_host(res);
+}
+
+// exact-size copies of every array of the device image into the result's host image
+int result_ensure_host(tagg_result* res) {
+    if (!res->has_img || !res->lazy) return 0;
+    if (!res->d_img) return tagg_fail(TAGG_ERR_BAD_ARG, "the device image of this result is gone");
+    const PlanMeta& m = *res->meta;
+    const size_t ns = res->n_scope.size(), nk = res->d_off_values.size();
+    CUDA_TRY(cudaSetDevice(res->ctx->device));
+    cudaStream_t st = res->d_stream;
+    {
+        const uint8_t* d_img = res->d_img;
+        const struct { const std::vector<size_t>&k, &p, &v, &s; } D{res->d_off_keys, res->d_off_parents, res->d_off_values, res->d_off_seen};
+        res->off_keys.assign(ns, 0); res->off_parents.assign(ns, 0);
+        res->off_values.assign(nk, 0); res->off_seen.assign(nk, 0);
         size_t off = al64(ns * 8);
         for (size_t s = 1; s < ns; s++) {
             res->off_keys[s] = off; off = al64(off + res->n_scope[s] * 8);
@@ -308,35 +343,23 @@ int compact_finish(ExecState& es, tagg_result* res) {
             res->off_values[k] = off; off = al64(off + n * 8);
             res->off_seen[k] = off; off = al64(off + n);
         }
-        std::vector<uint8_t> hdr(res->img, res->img + al64(ns * 8));
         int rc = result_reserve(res, off);
         if (rc) return rc;
-        memcpy(res->img, hdr.data(), hdr.size());
         for (size_t s = 1; s < ns; s++) {
             const uint64_t n = res->n_scope[s];
             if (!n) continue;
-            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_keys[s], C.d_img + C.d_off_keys[s], n * 8, cudaMemcpyDeviceToHost, es.st));
-            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_parents[s], C.d_img + C.d_off_parents[s], n * 4, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_keys[s], d_img + D.k[s], n * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_parents[s], d_img + D.p[s], n * 4, cudaMemcpyDeviceToHost, st));
         }
         for (size_t k = 0; k < nk; k++) {
             const uint64_t n = res->n_scope[m.scope_of[m.slot_node[k]]];
             if (!n) continue;
-            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_values[k], C.d_img + C.d_off_values[k], n * 8, cudaMemcpyDeviceToHost, es.st));
-            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_seen[k], C.d_img + C.d_off_seen[k], n, cudaMemcpyDeviceToHost, es.st));
+            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_values[k], d_img + D.v[k], n * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(res->img + res->off_seen[k], d_img + D.s[k], n, cudaMemcpyDeviceToHost, st));
         }
-        CUDA_TRY(cudaStreamSynchronize(es.st));
+        CUDA_TRY(cudaStreamSynchronize(st));
     }
-    res->has_img = true;
-    for (auto& sc : res->scopes) { sc.keys.clear(); sc.parents.clear(); }
-    for (auto& sl : res->slots) { sl.values.clear(); sl.seen.clear(); }
-    // the device image moves into the result: top_k / row reads run on it (released with the result)
-    res->release_device();
-    res->d_img = C.d_img;
-    res->d_bytes = C.d_bytes;
-    res->d_off_keys = C.d_off_keys;
-    res->d_off_values = C.d_off_values;
-    res->d_off_seen = C.d_off_seen;
-    C.d_img = nullptr;
+    res->lazy = false;
     return 0;
 }
 

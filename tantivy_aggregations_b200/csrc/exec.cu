@@ -813,6 +813,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             rc = comm_merge_arena(es, mode == 2 ? root : -1);
             if (rc) return rc;
         }
+        rc = pct_rank_prefetch(es);
+        if (rc) return rc;
         uint32_t* flags = (uint32_t*)const_cast<void*>(es.pin(nullptr, 16));  // [overflow][bad ids]
         uint32_t flags_local[4] = {0, 0, 0, 0};
         if (!flags) flags = flags_local;
@@ -863,6 +865,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             // a column that spans both zeros: the order of the codes picked -0.0 as the minimum (+0.0 as the maximum); if
             // the other zero was collected too the reference keeps whichever came FIRST (minmax.rs:99-102) — exact path
             if (!es.edge_exact && edge_straddle && !collective) {
+                rc = result_ensure_host(res);
+                if (rc) return rc;
                 bool ambiguous = false;
                 for (size_t k = 0; k < es.slot_edge.size() && !ambiguous; k++) {
                     if (es.slot_edge[k] != 1) continue;
@@ -881,7 +885,16 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
             if (!redo) break;
         }
         drop_result();
-        if (overflow == 3) es.no_rank = true;  // the rank bins could not resolve this distribution: exact path
+        if (overflow == 3) {  // the rank bins could not resolve this distribution
+            bool cached = false;
+            for (int k = 0; k < 4; k++) cached = cached || (es.rank[k].active && es.rank[k].from_cache);
+            if (cached) {  // ... with thresholds remembered from another docset: sample this one afresh
+                std::lock_guard<std::mutex> g(plan->mu);
+                for (auto& pc : plan->pct_cache) pc.valid = false;
+            } else {
+                es.no_rank = true;  // exact path
+            }
+        }
         if (overflow == 2) return rc = tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
         if (overflow == 4) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
         if (overflow == 5) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");

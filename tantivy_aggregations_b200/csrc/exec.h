@@ -52,7 +52,7 @@ struct CompactState {
     std::vector<uint64_t> cap_scope;
     std::vector<size_t> d_off_keys, d_off_parents, d_off_values, d_off_seen;
     std::vector<uint32_t*> d_rank;  // per scope: compact index of every raw cell (only where a child scope / nested percentile needs it)
-    bool one_shot = false, launched = false;
+    bool one_shot = false, launched = false, lazy = false;
 };
 
 struct ExecState {
@@ -100,6 +100,9 @@ struct ExecState {
         uint64_t* d_tail = nullptr;
         uint64_t tail_cap = 0;
         PctSummary summary;          // filled by pct_rank_collect
+        bool from_cache = false;     // thresholds reused from the plan (no sample pass)
+        uint32_t node = 0;
+        const uint8_t* h_block = nullptr;  // pinned copy of d_block, in flight before the pass's sync (pct_rank_prefetch)
     } rank[4];
     bool no_rank = false;            // a rank-bin pass failed its precision check: redo on the exact path
     // f64 MIN / MAX follow the reference's PartialOrd fold (minmax.rs:97-106): per slot, 0 = the order of the codes is
@@ -158,5 +161,6 @@ int mterms_try(ExecState& es);
 // pct.cu: percentiles on the streaming path.  plan: 1 = rank-bin mode configured in es.rank[k], 0 = use the exact
 // path, <0 = -status.  collect (after the pass, synchronises): 1 = summary ready, 0 = precision check failed.
 int pct_rank_plan(ExecState& es, uint32_t node, int k);
+int pct_rank_prefetch(ExecState& es);  // after the pass, before its sync: start the download of the bin tables
 int pct_rank_collect(ExecState& es, int k);
 void pct_rank_release(ExecState& es);

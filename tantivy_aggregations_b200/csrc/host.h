@@ -111,9 +111,25 @@ struct PlanMeta {
     std::vector<std::vector<uint8_t>> blobs;
 };
 
+// percentiles on the streaming path (pct.cu): the rank-bin thresholds a sample pass found for (plan, segment set).  They
+// only steer efficiency — every pass verifies its own precision on the real counts — so repeated queries reuse them and
+// skip the sample kernel, its sort and the host round trip.
+struct PctThresholds {
+    bool valid = false;
+    std::vector<const void*> segs;
+    uint32_t node = 0;
+    uint64_t lo = 0, span = 0;
+    uint32_t shift = 0, mul = 0, n_bins = 0;
+    bool linear = false;
+    double f_lo = 0, f_scale = 0;
+    uint64_t tail_seen = 0;  // values that went to the exact lists last time (sizes the next list)
+};
+
 struct tagg_plan {
     tagg_ctx* ctx = nullptr;
     std::shared_ptr<PlanMeta> meta;
+    mutable PctThresholds pct_cache[4];  // guarded by mu
+    int readout = 0;                     // TAGG_READOUT_*
     std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
     // multi-GPU: the key domains agreed across ranks on the previous collective call of this plan; reused optimistically
     // and re-verified by every call's own agreement (exec.cu)
@@ -146,8 +162,8 @@ struct tagg_result {
     uint8_t* d_img = nullptr;
     size_t d_bytes = 0;
     cudaStream_t d_stream = nullptr;
-    std::vector<size_t> d_off_keys, d_off_values, d_off_seen;
-    bool lazy = false;  // arrays were not downloaded (TAGG_READOUT_LAZY): readers fetch on demand
+    std::vector<size_t> d_off_keys, d_off_parents, d_off_values, d_off_seen;
+    bool lazy = false;  // arrays were not downloaded yet (TAGG_READOUT_LAZY): result_ensure_host fetches them on demand
     struct Scope { std::vector<uint64_t> keys; std::vector<uint32_t> parents; };
     struct Slot { std::vector<uint64_t> values; std::vector<uint8_t> seen; };
     std::vector<Scope> scopes;   // by scope id
@@ -185,3 +201,5 @@ cudaError_t launch_ids_to_bitset(const uint32_t* ids, uint64_t n, uint32_t* word
 
 // result.cu
 int result_merge(tagg_result* dst, const tagg_result* src);
+// compact.cu: a lazily read result downloads its arrays on first use
+int result_ensure_host(tagg_result* res);

@@ -80,6 +80,33 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
     const uint64_t n_docs = begin[nseg];
     if (n_docs < PCT_MIN_DOCS) return 0;
 
+    {   // thresholds of an earlier call on the same (plan, segment set): no sample pass
+        std::lock_guard<std::mutex> g(es.plan->mu);
+        const PctThresholds& pc = es.plan->pct_cache[k];
+        if (pc.valid && pc.node == node && pc.segs.size() == nseg && std::equal(pc.segs.begin(), pc.segs.end(), es.segs.begin(), [](const void* a, const tagg_segment* b) { return a == (const void*)b; })) {
+            ExecState::RankState& R = es.rank[k];
+            R = ExecState::RankState();
+            R.lo = pc.lo; R.span = pc.span; R.shift = pc.shift; R.mul = pc.mul; R.n_bins = pc.n_bins;
+            R.linear = pc.linear; R.f_lo = pc.f_lo; R.f_scale = pc.f_scale;
+            R.from_cache = true;
+            R.node = node;
+            R.tail_cap = pc.tail_seen * 2 + (1u << 18);
+            const size_t blk = 16 + (size_t)R.n_bins * 25;
+            if (cudaMallocAsync((void**)&R.d_block, blk, es.st) == cudaSuccess && cudaMallocAsync((void**)&R.d_tail, R.tail_cap * 8 + 16, es.st) == cudaSuccess &&
+                cudaMemsetAsync(R.d_block, 0, blk, es.st) == cudaSuccess) {
+                R.d_tail_count = (unsigned long long*)R.d_block;
+                R.d_count = (uint64_t*)(R.d_block + 16);
+                R.d_min = R.d_count + R.n_bins;
+                R.d_max = R.d_min + R.n_bins;
+                R.d_present = (uint8_t*)(R.d_max + R.n_bins);
+                R.active = true;
+                return 1;
+            }
+            cudaGetLastError();
+            pct_rank_release(es);
+        }
+    }
+
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
     uint32_t first = 0;
@@ -206,6 +233,7 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
     R = ExecState::RankState();
     R.lo = lo; R.span = span; R.shift = shift; R.mul = mul; R.n_bins = n_bins;
     R.linear = linear; R.f_lo = f_lo; R.f_scale = f_scale;
+    R.node = node;
     // values outside [lo, hi): the sampled share below lo, plus what lies above the largest sampled value
     R.tail_cap = (uint64_t)(n_est * ((double)(j_lo + (mm - j_hi)) / (double)mm) * 1.5) + (uint64_t)(n_est / mm * 64) + (1u << 18);
     const size_t blk = 16 + (size_t)n_bins * 25;
@@ -238,15 +266,35 @@ static void rank_schedule(uint64_t n, std::vector<uint64_t>& ranks) {
     }
 }
 
+// the bin tables (count / min / max per bin + the list counters) start their way to pinned host memory right behind the
+// pass, so that the pass's own synchronisation delivers them
+int pct_rank_prefetch(ExecState& es) {
+    for (auto& R : es.rank) {
+        if (!R.active || !R.d_block) continue;
+        const size_t bytes = 16 + (size_t)R.n_bins * 24;
+        uint8_t* h = (uint8_t*)const_cast<void*>(es.pin(nullptr, bytes));
+        R.h_block = nullptr;
+        if (!h) continue;
+        CUDA_TRY(cudaMemcpyAsync(h, R.d_block, bytes, cudaMemcpyDeviceToHost, es.st));
+        R.h_block = h;
+    }
+    return 0;
+}
+
 int pct_rank_collect(ExecState& es, int k) {
     ExecState::RankState& R = es.rank[k];
     const uint32_t nb = R.n_bins;
-    std::vector<uint8_t> blk(16 + (size_t)nb * 24);
-    CUDA_TRY(cudaMemcpyAsync(blk.data(), R.d_block, blk.size(), cudaMemcpyDeviceToHost, es.st));
-    CUDA_TRY(cudaStreamSynchronize(es.st));
+    std::vector<uint8_t> blk_copy;
+    const uint8_t* blk = R.h_block;
+    if (!blk) {
+        blk_copy.resize(16 + (size_t)nb * 24);
+        CUDA_TRY(cudaMemcpyAsync(blk_copy.data(), R.d_block, blk_copy.size(), cudaMemcpyDeviceToHost, es.st));
+        CUDA_TRY(cudaStreamSynchronize(es.st));
+        blk = blk_copy.data();
+    }
     unsigned long long tc[2];
-    memcpy(tc, blk.data(), 16);
-    const uint64_t* cnt = (const uint64_t*)(blk.data() + 16);
+    memcpy(tc, blk, 16);
+    const uint64_t* cnt = (const uint64_t*)(blk + 16);
     const uint64_t* mn = cnt + nb;  // max-form: ~code
     const uint64_t* mx = mn + nb;
     const uint64_t n_tail = tc[0], n_low = tc[1];
@@ -322,6 +370,16 @@ int pct_rank_collect(ExecState& es, int k) {
             if (cnt[b] > 1) { S.ranks.push_back(below + cnt[b]); S.value_bits.push_back(code_to_f64_bits(mx[b])); }
             below += cnt[b];
         }
+    }
+    {   // remember the thresholds for the next query on this (plan, segment set)
+        std::lock_guard<std::mutex> g(es.plan->mu);
+        PctThresholds& pc = es.plan->pct_cache[k];
+        pc.valid = true;
+        pc.segs.assign(es.segs.begin(), es.segs.end());
+        pc.node = R.node;
+        pc.lo = R.lo; pc.span = R.span; pc.shift = R.shift; pc.mul = R.mul; pc.n_bins = R.n_bins;
+        pc.linear = R.linear; pc.f_lo = R.f_lo; pc.f_scale = R.f_scale;
+        pc.tail_seen = n_tail;
     }
     return 1;
 }

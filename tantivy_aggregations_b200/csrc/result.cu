@@ -177,6 +177,7 @@ int read_percentiles(ExecState& es, tagg_result* res) {
 // ---- the two representations of a result (host.h) ----------------------------------------------------------------
 void tagg_result::materialize() {
     if (!has_img) return;
+    result_ensure_host(this);
     const size_t ns = n_scope.size(), nk = off_values.size();
     scopes.resize(ns);
     slots.resize(nk);
@@ -280,6 +281,10 @@ int result_merge(tagg_result* dst, const tagg_result* src) {
     size_t ns = m.scope_node.size();
     if (dst->merged_elsewhere || src->merged_elsewhere) return tagg_fail(TAGG_ERR_BAD_ARG, "the fruit of a tagg_execute_reduce call lives on the root rank only");
     dst->materialize();
+    {
+        int rce = result_ensure_host(const_cast<tagg_result*>(src));
+        if (rce) return rce;
+    }
     auto shaped = [&](const tagg_result* r) {
         if (r->pcts.size() != m.pct_node.size()) return false;
         if (r->has_img) return r->n_scope.size() == ns && r->off_values.size() == m.slot_node.size();
@@ -365,6 +370,7 @@ int tagg_result_scope_len(const tagg_result* res, uint32_t scope_node, uint64_t*
 }
 
 int tagg_result_scope_read(const tagg_result* res, uint32_t scope_node, uint64_t* keys, uint32_t* parents, uint64_t cap) {
+    if (res) { int rce = result_ensure_host(const_cast<tagg_result*>(res)); if (rce) return rce; }
     if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     int s = scope_index(res, scope_node);
     if (s < 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
@@ -385,6 +391,7 @@ int tagg_result_metric_len(const tagg_result* res, uint32_t node, uint64_t* n_bu
 }
 
 int tagg_result_metric_read(const tagg_result* res, uint32_t node, uint64_t* values, uint8_t* seen, uint64_t cap) {
+    if (res) { int rce = result_ensure_host(const_cast<tagg_result*>(res)); if (rce) return rce; }
     if (!res) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
         return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);
@@ -397,6 +404,7 @@ int tagg_result_metric_read(const tagg_result* res, uint32_t node, uint64_t* val
 }
 
 int tagg_result_scope_view(const tagg_result* res, uint32_t scope_node, const uint64_t** keys, const uint32_t** parents, uint64_t* n) {
+    if (res) { int rce = result_ensure_host(const_cast<tagg_result*>(res)); if (rce) return rce; }
     if (!res || !n) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     int s = scope_index(res, scope_node);
     if (s <= 0) return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a bucket aggregation", scope_node);
@@ -407,6 +415,7 @@ int tagg_result_scope_view(const tagg_result* res, uint32_t scope_node, const ui
 }
 
 int tagg_result_metric_view(const tagg_result* res, uint32_t node, const uint64_t** values, const uint8_t** seen, uint64_t* n) {
+    if (res) { int rce = result_ensure_host(const_cast<tagg_result*>(res)); if (rce) return rce; }
     if (!res || !n) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
     if (node >= res->meta->nodes.size() || res->meta->slot_of[node] < 0)
         return tagg_fail(TAGG_ERR_BAD_ARG, "node %u is not a count/sum/min/max leaf", node);

@@ -380,6 +380,27 @@ class ResultReader:
         F.check(F.lib().tagg_result_metric_view(self._h, node, C.byref(v), C.byref(s), C.byref(n)))
         return self._view(v.value, n.value, np.uint64), self._view(s.value, n.value, np.uint8)
 
+    def top_k(self, scope_node, by_node, k, parent_bucket=0):
+        """Bucket indices of `Terms::top_k(k, |b| b.<leaf by_node>)` (terms.rs:425-457), selected on the device."""
+        out = np.zeros(max(int(k), 1), dtype=np.uint32)
+        n = C.c_uint64()
+        F.check(F.lib().tagg_result_top_k(self._h, int(scope_node), int(parent_bucket), int(by_node), int(k), _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def scope_rows(self, node, buckets):
+        buckets = np.ascontiguousarray(buckets, dtype=np.uint32)
+        keys = np.zeros(len(buckets), dtype=np.uint64)
+        parents = np.zeros(len(buckets), dtype=np.uint32)
+        F.check(F.lib().tagg_result_scope_rows(self._h, int(node), _ptr(buckets) if len(buckets) else None, len(buckets), _ptr(keys), _ptr(parents)))
+        return keys, parents
+
+    def metric_rows(self, node, buckets):
+        buckets = np.ascontiguousarray(buckets, dtype=np.uint32)
+        values = np.zeros(len(buckets), dtype=np.uint64)
+        seen = np.zeros(len(buckets), dtype=np.uint8)
+        F.check(F.lib().tagg_result_metric_rows(self._h, int(node), _ptr(buckets) if len(buckets) else None, len(buckets), _ptr(values), _ptr(seen)))
+        return values, seen
+
     def is_local(self):
         """False on the non-root ranks of a tagg_execute_reduce call: the fruit lives on the root."""
         out = C.c_int()
@@ -440,6 +461,25 @@ class ResultReader:
             pass
 
 
+class _RowsReader:
+    """A reader over k gathered rows of one scope: lets `Agg.decode` build the sub-fruits of just those buckets."""
+
+    def __init__(self, reader, buckets):
+        self.reader, self.buckets = reader, buckets
+        self._metrics = {}
+
+    def metric(self, node):
+        if node not in self._metrics:
+            self._metrics[node] = self.reader.metric_rows(node, self.buckets)
+        return self._metrics[node]
+
+    def scope_children(self, node, parent_bucket):
+        raise NotImplementedError("top_k on the device decodes buckets whose sub-aggregation is count / sum / min / max leaves")
+
+    def percentiles(self, node, bucket):
+        raise NotImplementedError("top_k on the device decodes buckets whose sub-aggregation is count / sum / min / max leaves")
+
+
 class Plan:
     """A lowered aggregation tree resident as a tagg_plan (the `PreparedAgg`, src/agg.rs:19-28)."""
 
@@ -461,6 +501,9 @@ class Plan:
     @property
     def filters(self):
         return self.lctx.filters
+
+    def set_readout(self, mode):
+        F.check(F.lib().tagg_plan_set_readout(self._h, int(mode)))
 
     def close(self):
         if self._h:
@@ -523,6 +566,28 @@ class Searcher:
 
     def prepare(self, agg):
         return Plan(self.ctx, agg, self)
+
+    def terms_top_k(self, query, agg, terms, by, k):
+        """agg_search followed by `Terms::top_k(k, |b| <leaf `by`>)` on the fruit of the top-level `terms` node of `agg`
+        (terms.rs:425-457) — with the selection on the GPU and only the k winning buckets read back (lazy read-out).
+        `terms`: the TermsAgg inside `agg`; `by`: one of its leaf sub-aggregations (count / sum / min / max).
+        Returns [(key, sub fruit)] in the reference's order: sort value descending, key ascending."""
+        plan = self.prepare(agg)
+        plan.set_readout(F.READOUT_LAZY)
+        arr, keep = build_inputs(plan, query, self.segments)
+        h = C.c_void_p()
+        F.check(F.lib().tagg_execute(plan._h, arr, len(self.segments), C.byref(h)))
+        reader = ResultReader(h)
+        buckets = reader.top_k(terms.node, by.node, k)
+        keys, _ = reader.scope_rows(terms.node, buckets)
+        rows = _RowsReader(reader, buckets)
+        out = []
+        for i, kb in enumerate(keys.tolist()):
+            key = codec.bits_to_value(terms.kind, kb)
+            if terms.key_filter is not None and not terms.key_filter(key):
+                continue
+            out.append((key, terms.sub.decode(rows, i)))
+        return out
 
     def agg_search(self, query, agg):
         """src/searcher.rs:13-17 — default executor is SingleThread."""
