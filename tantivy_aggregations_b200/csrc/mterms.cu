@@ -18,6 +18,7 @@
 // itself captures any reuse, so the floor of this kernel is the L2 atomic unit, not HBM
 // (profiles/r1_atom_bench_b200.txt: 190 G RED.F64/s on 10^6 addresses).  Bucket-existence / Option flags
 // are filtered through a CTA-private bitmap in shared memory so an occurrence costs no global load.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -26,7 +27,7 @@
 #include "narrow.cuh"
 
 #define MT_SUB_THREADS 256
-#define MT_MAXSUB 3     // sub-blocks per CTA: 768 threads leave 80 registers per thread (64 spilled ~100 bytes per thread)
+#define MT_MAXSUB 4
 #define MT_TILE 1024     // documents per sub-block tile
 #define MT_TILE_BITS 10
 #define MT_CHUNK 4096    // key occurrences expanded at a time
@@ -35,7 +36,7 @@
 #define MT_MAXCOUNTS 2
 #define MT_U 4           // key occurrences in flight per thread (8 spills)
 #define MT_DU (MT_TILE / MT_SUB_THREADS)  // documents per thread in the doc phase
-#define MT_CACHE_LOG 10  // hot-key front: 2^10 entries per CTA
+#define MT_CACHE_LOG 9   // hot-key front: 2^9 entries per CTA (10.5 KB: four sub-blocks and the 1 M-key bitmap still fit)
 #define MT_CACHE_EMPTY 0xFFFFFFFFFFFFFFFFull
 
 enum { MO_SUM = 1, MO_MIN = 2, MO_MAX = 4 };
@@ -61,7 +62,6 @@ struct MGroup {
     uint32_t derive_op;   // SEEN_DERIVED: the op whose accumulator tells (MO_MIN / MO_MAX: cell != 0; MO_SUM f64: cell != -0.0)
     uint32_t soff_sum, soff_min, soff_max;  // per-document folded contribution, offsets inside a sub-block's shared block
 };
-#define MT_NCOLS (2 + 2 * MT_MAXGROUPS)
 struct MParams {
     const DevSegment* segs;       // all segments of the call
     const uint32_t* tile_begin;   // n_segs + 1 tile offsets
@@ -76,71 +76,26 @@ struct MParams {
     int32_t n_groups;
     MGroup groups[MT_MAXGROUPS];
     uint32_t present_mode;   // PRESENT_*
-    uint32_t present_from_seen;  // PRESENT_EXPLICIT: group 0's derived Option flags imply bucket existence (fixup ORs them in)
     uint32_t bitmap_bytes;   // PRESENT_BITMAP: CTA-private bucket-existence bitmap in shared memory
     uint32_t cache_bytes;    // hot-key front (CACHE instantiations): [keys u64][sums u64][counts u32][touched u8] x 2^MT_CACHE_LOG
     uint32_t sub_bytes;      // shared bytes per sub-block
-    uint32_t soff_koff, soff_docof, soff_flags, soff_cols, soff_mbar;
-    // per-tile slices of the packed columns staged into the sub-block's shared memory by TMA bulk copies (slot 0: key
-    // offsets, 1: key values, 2 + 2g / 3 + 2g: offsets / values of leaf group g); 0 bytes = read from global memory
-    uint32_t soff_sbuf[MT_NCOLS], sbuf_bytes[MT_NCOLS];
+    uint32_t soff_koff, soff_docof, soff_flags, soff_cols;
 };
 
 __device__ __forceinline__ void named_bar(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ uint32_t mt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mt_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mt_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mt_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mt_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mt_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mt_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mt_mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(mt_smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mt_tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mt_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(mt_smem_u32(bar))
-                 : "memory");
-}
 
-// Column descriptors, cached in the sub-block's shared memory: cg[] = the current segment's columns in global memory,
-// cs[] = where the CURRENT TILE reads them — a view of the slice staged in shared memory (`words` is then the generic
-// address of the staging buffer minus the slice's byte offset, so value indices stay absolute) or the global column.
-// Both words of a value are always fetched (allocations are padded, dev.cuh; slices carry 16 spare bytes), so the two
-// loads are independent and nothing branches on the straddle.
+// Column descriptors of the current segment, cached in the sub-block's shared memory (slot 0: key offsets,
+// 1: key values, 2 + 2g / 3 + 2g: offsets / values of leaf group g).  Both words of a value are always
+// fetched (the allocation is padded, dev.cuh), so the two loads are independent and nothing branches on
+// the straddle.
 struct ColS {
-    const uint64_t* words;  // global column (cg[]; cs[] of a slot that is not staged)
+    const uint64_t* words;
     uint64_t minv, mask;
-    uint32_t nb;
-    uint32_t saddr;         // staged view: shared-memory address of the slice minus its byte offset (mod 2^32); 0 = read `words`
+    uint32_t nb, pad;
 };
-__device__ __forceinline__ uint32_t mt_lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-// (explicit ld.shared: a generic-pointer load of staged data would be tracked like a global load)
+#define MT_NCOLS (2 + 2 * MT_MAXGROUPS)
 __device__ __forceinline__ uint64_t cget(const ColS& c, uint64_t i) {
     const uint64_t bit = i * c.nb;
-    if (c.saddr) {  // staged in shared memory: 32-bit words (byte offsets < 2^32: a column is at most 2^32 values of <= 64 bits... taken mod 2^32 like saddr)
-        const uint32_t a = c.saddr + (uint32_t)((bit >> 5) << 2), sh = (uint32_t)bit & 31u;
-        const uint32_t w0 = mt_lds32(a), w1 = mt_lds32(a + 4);
-        uint64_t v = __funnelshift_r(w0, w1, sh);
-        if (c.nb > 32) v |= (uint64_t)__funnelshift_r(w1, mt_lds32(a + 8), sh) << 32;
-        return (v & c.mask) + c.minv;
-    }
     if (c.nb <= 32) {  // narrow columns (keys, offsets): 32-bit words and one funnel shift
         const uint32_t* w32 = (const uint32_t*)c.words + (bit >> 5);
         const uint32_t lo = __ldg(w32), hi = __ldg(w32 + 1);
@@ -162,14 +117,14 @@ __device__ __forceinline__ void l2_prefetch_values(const ColS& c, uint64_t lo, u
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((uint32_t)bytes) : "memory");
 }
 __device__ __forceinline__ void cols_load(ColS* dst, const DevColumn& c) {
-    dst->words = c.words; dst->minv = c.min_value; dst->mask = c.mask; dst->nb = c.num_bits; dst->saddr = 0;
+    dst->words = c.words; dst->minv = c.min_value; dst->mask = c.mask; dst->nb = c.num_bits; dst->pad = 0;
 }
 
 // CACHE: the shared-memory hash front of north_star (4) — a CTA-private table of (key -> partial count / partial sum), first
 // come first served, in front of the global table: a hot key of a skewed distribution is folded on chip and reaches the
-// global table (where same-address atomics serialise in L2) once per CTA.  Keys that find their slot taken go straight
-// to the global table.  For shapes with at most one count and one sum-only leaf group (CACHE instantiations also drop the
-// min / max paths at compile time: the kernel is register-bound).
+// global table (where same-address atomics serialise in L2: 3 % of 10^9 updates on ONE cell took 48 ms) once per CTA.
+// Keys that find their slot taken go straight to the global table.  For shapes with at most one count and one sum-only
+// leaf group.
 template <bool DENSE, int NG, int NC, bool CACHE>
 __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const __grid_constant__ MParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -184,9 +139,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
     uint32_t* koff = (uint32_t*)(base + p.soff_koff);    // MT_TILE + 1 key offsets relative to the tile's first key
     uint16_t* docof = (uint16_t*)(base + p.soff_docof);  // MT_CHUNK tile-local document indices
     uint8_t* flags = base + p.soff_flags;                // per document: bit 0 matched, bit 1 + g contributes to group g
-    ColS* cs = (ColS*)(base + p.soff_cols);              // [MT_NCOLS] views of the current tile, then [MT_NCOLS] global columns
-    ColS* cg = cs + MT_NCOLS;
-    uint64_t* mbar = (uint64_t*)(base + p.soff_mbar);
+    ColS* cs = (ColS*)(base + p.soff_cols);
     const bool has_bitmap = DENSE && p.present_mode == PRESENT_BITMAP;
     if (has_bitmap)
         for (uint32_t i = tid; i < p.bitmap_bytes / 4; i += blockDim.x) bitmap[i] = 0;
@@ -197,65 +150,32 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             ccnt[i] = 0;
             ctouch[i] = 0;
         }
-    if (st == 0) {
-        mt_mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-    uint32_t cur_seg = 0xffffffffu, seg = 0, mb_parity = 0;
+    uint32_t cur_seg = 0xffffffffu, seg = 0;
+    // the front pays only for skewed keys: every sub-block measures its hit rate over its first two tiles and stops
+    // probing below 1/16 (uniform keys over a large domain: ~10 % of the kernel for nothing); cached entries stay valid
+    bool use_cache = CACHE;
+    uint32_t n_probe = 0, n_hit = 0, tiles_done = 0;
+    uint32_t* cstat = (uint32_t*)(ctouch + (1u << MT_CACHE_LOG)) + 2 * sub;  // [probes, hits] of this sub-block
+    if (CACHE && st == 0) { cstat[0] = 0; cstat[1] = 0; }
     const uint64_t dom_min = p.scope.dom_min, dom_size = p.scope.dom_size;
-    const uint32_t n_slices = 2 + 2 * NG;
 
     for (uint64_t tile = (uint64_t)blockIdx.x * n_sub + sub; tile < p.n_tiles; tile += (uint64_t)gridDim.x * n_sub) {
         while (seg + 1 < p.n_segs && __ldg(p.tile_begin + seg + 1) <= (uint32_t)tile) seg++;
         const DevSegment& S = p.segs[seg];
-        named_bar(1 + sub, MT_SUB_THREADS);  // everybody is done with the previous tile's staged slices and descriptors
         if (seg != cur_seg) {  // uniform over the sub-block: refresh the cached column descriptors
-            if (st == 0) cols_load(cg + 0, S.cols[p.key_col]);
-            if (st == 1) cols_load(cg + 1, S.cols[p.key_multi ? p.key_col + 1 : p.key_col]);
-            if (st >= 2 && st < n_slices) {
+            named_bar(1 + sub, MT_SUB_THREADS);
+            if (st == 0) cols_load(cs + 0, S.cols[p.key_col]);
+            if (st == 1) cols_load(cs + 1, S.cols[p.key_multi ? p.key_col + 1 : p.key_col]);
+            if (st >= 2 && st < 2 + 2 * NG) {
                 const MGroup& G = p.groups[(st - 2) >> 1];
-                cols_load(cg + st, S.cols[G.multi ? G.col + ((st - 2) & 1) : G.col]);
+                cols_load(cs + st, S.cols[G.multi ? G.col + ((st - 2) & 1) : G.col]);
             }
             named_bar(1 + sub, MT_SUB_THREADS);
             cur_seg = seg;
         }
         const uint32_t d0 = ((uint32_t)tile - __ldg(p.tile_begin + seg)) * MT_TILE;
         const uint32_t nd = min((uint32_t)MT_TILE, S.max_doc - d0);
-        // ---- stage this tile's slices: lane c of warp 0 owns column slot c ------------------------------------------
-        //      value range of the slot -> 16-byte aligned byte range -> one TMA bulk copy into the slot's buffer (if it
-        //      fits; else the tile reads that column from global memory) -> publish the view
-        if (st < 32) {
-            uint32_t issued = 0;
-            if (st < n_slices) {
-                const bool is_vals = st & 1;
-                const bool multi = st < 2 ? p.key_multi != 0 : p.groups[(st - 2) >> 1].multi != 0;
-                ColS view = cg[st];
-                if (multi || is_vals) {  // (the offsets slot of a single-valued field is unused)
-                    uint64_t v0, v1;
-                    if (!is_vals) { v0 = d0; v1 = (uint64_t)d0 + nd + 1; }
-                    else if (multi) { v0 = cget(cg[st - 1], d0); v1 = cget(cg[st - 1], (uint64_t)d0 + nd); }
-                    else { v0 = d0; v1 = (uint64_t)d0 + nd; }
-                    const uint64_t b0 = ((v0 * view.nb) >> 3) & ~(uint64_t)15;
-                    const uint64_t b1 = ((((v1 * view.nb + 7) >> 3) + 16 + 15) & ~(uint64_t)15);
-                    if (view.nb && v1 > v0 && b1 - b0 <= p.sbuf_bytes[st] && b1 < 0xffffff00ull) {
-                        uint8_t* dst = base + p.soff_sbuf[st];
-                        mt_tma_g2s(dst, (const uint8_t*)view.words + b0, (uint32_t)(b1 - b0), mbar);
-                        issued = (uint32_t)(b1 - b0);
-                        view.saddr = mt_smem_u32(dst) - (uint32_t)b0;  // (mod 2^32) absolute value indices keep working
-                    }
-                }
-                cs[st] = view;
-            }
-            const uint32_t bytes = __reduce_add_sync(0xffffffffu, issued);
-            if (st == 0) {
-                if (bytes) mt_mbar_expect_tx(mbar, bytes);
-                else mt_mbar_arrive(mbar);
-            }
-        }
-        named_bar(1 + sub, MT_SUB_THREADS);  // views published
-        mt_mbar_wait(mbar, mb_parity);       // bytes landed
-        mb_parity ^= 1u;
         const uint64_t kbase = p.key_multi ? cget(cs[0], d0) : (uint64_t)d0;
         const bool plain = S.main.kind == DS_ALL && !S.has_deletes && p.n_preds == 0;
         // ---- L2 prefetch of the sub-block's NEXT tile: fixed-position slices (offset columns) now, the
@@ -263,16 +183,16 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
         const uint64_t ntile = tile + (uint64_t)gridDim.x * n_sub;
         uint64_t pf_lo = 0, pf_hi = 0;  // lanes 1 / 3 + 2g of warp 0: value range of the next tile
         int pf_col = -1;
-        if (st < n_slices && ntile < p.n_tiles && ntile < __ldg(p.tile_begin + seg + 1)) {
+        if (st < 2 + 2 * NG && ntile < p.n_tiles && ntile < __ldg(p.tile_begin + seg + 1)) {
             const uint32_t nd0 = ((uint32_t)ntile - __ldg(p.tile_begin + seg)) * MT_TILE;
             const uint32_t nnd = min((uint32_t)MT_TILE, S.max_doc - nd0);
             const bool is_vals = st & 1;
             const bool multi = st < 2 ? p.key_multi != 0 : p.groups[(st - 2) >> 1].multi != 0;
             if (!is_vals) {
-                if (multi) l2_prefetch_values(cg[st], nd0, (uint64_t)nd0 + nnd + 1);
+                if (multi) l2_prefetch_values(cs[st], nd0, (uint64_t)nd0 + nnd + 1);
             } else {
                 pf_col = (int)st;
-                if (multi) { pf_lo = cget(cg[st - 1], nd0); pf_hi = cget(cg[st - 1], (uint64_t)nd0 + nnd); }
+                if (multi) { pf_lo = cget(cs[st - 1], nd0); pf_hi = cget(cs[st - 1], (uint64_t)nd0 + nnd); }
                 else { pf_lo = nd0; pf_hi = (uint64_t)nd0 + nnd; }
             }
         }
@@ -303,7 +223,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 const MGroup& G = p.groups[g];
-                const ColS vc = cs[3 + 2 * g];
+                const ColS& vc = cs[3 + 2 * g];
                 uint64_t sum[MT_DU], mn[MT_DU], mx[MT_DU];  // min in max-form (~code), like the arena
 #pragma unroll
                 for (int u = 0; u < MT_DU; u++) { sum[u] = G.kind == TAGG_F64 ? NEG_ZERO_BITS : 0ull; mn[u] = 0; mx[u] = 0; }  // f64 sums fold from -0.0
@@ -324,20 +244,17 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                             if (G.kind == TAGG_F64) sum[u] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)sum[u]), code_to_f64(code[u])));
                             else sum[u] += code_to_bits(G.kind, code[u]);
                         }
-                        if (!CACHE && (G.ops & MO_MIN)) mn[u] = max(mn[u], ~code[u]);
-                        if (!CACHE && (G.ops & MO_MAX)) mx[u] = max(mx[u], code[u]);
+                        if (G.ops & MO_MIN) mn[u] = max(mn[u], ~code[u]);
+                        if (G.ops & MO_MAX) mx[u] = max(mx[u], code[u]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < MT_DU; u++) {
                     if (fl[u] && ge[u][g] > ga[u][g]) {
                         fl[u] |= 2u << g;
-                        // a contribution equal to the identity of the accumulator that the Option flag is derived from leaves no
-                        // trace in the cell: remember it (bit 3 + g) so that the value phase sets the flag explicitly
-                        if (G.seen_mode == SEEN_DERIVED && ((CACHE || G.derive_op == MO_SUM) ? sum[u] == NEG_ZERO_BITS : G.derive_op == MO_MIN ? mn[u] == 0 : mx[u] == 0)) fl[u] |= 8u << g;
                         if (G.ops & MO_SUM) ((uint64_t*)(base + G.soff_sum))[di_[u]] = sum[u];
-                        if (!CACHE && (G.ops & MO_MIN)) ((uint64_t*)(base + G.soff_min))[di_[u]] = mn[u];
-                        if (!CACHE && (G.ops & MO_MAX)) ((uint64_t*)(base + G.soff_max))[di_[u]] = mx[u];
+                        if (G.ops & MO_MIN) ((uint64_t*)(base + G.soff_min))[di_[u]] = mn[u];
+                        if (G.ops & MO_MAX) ((uint64_t*)(base + G.soff_max))[di_[u]] = mx[u];
                     }
                 }
             }
@@ -345,7 +262,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             for (int u = 0; u < MT_DU; u++)
                 if (di_[u] < nd) flags[di_[u]] = (uint8_t)fl[u];
         }
-        if (pf_col >= 0) l2_prefetch_values(cg[pf_col], pf_lo, pf_hi);
+        if (pf_col >= 0) l2_prefetch_values(cs[pf_col], pf_lo, pf_hi);
         named_bar(1 + sub, MT_SUB_THREADS);
         const uint32_t nk = koff[nd];
         for (uint32_t cbase = 0; cbase < nk; cbase += MT_CHUNK) {
@@ -358,12 +275,10 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                 for (uint32_t v = lo; v < hi; v++) docof[v - cbase] = e;
             }
             named_bar(1 + sub, MT_SUB_THREADS);
-            const ColS kc = cs[1];
-            const uint32_t knb = kc.nb, kmask = (uint32_t)kc.mask;
+            const uint32_t knb = cs[1].nb, kmask = (uint32_t)cs[1].mask;
             const bool k32 = knb >= 1 && knb <= 32;
-            const uint64_t kminv = kc.minv, kbit0 = (kbase + cbase) * knb;
-            const uint32_t* kwp = (const uint32_t*)kc.words + (kbit0 >> 5);
-            const uint32_t ksa = kc.saddr + (uint32_t)((kbit0 >> 5) << 2);
+            const uint64_t kminv = cs[1].minv, kbit0 = (kbase + cbase) * knb;
+            const uint32_t* kwp = (const uint32_t*)cs[1].words + (kbit0 >> 5);
             const uint32_t ksh0 = (uint32_t)kbit0 & 31u;
             // ---- value phase: one thread per key occurrence (terms.rs:172-179), MT_U occurrences in flight ---
             for (uint32_t v0 = st; v0 < cn; v0 += MT_SUB_THREADS * MT_U) {
@@ -377,27 +292,27 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                     f[u] = v0 + u * MT_SUB_THREADS < cn ? e >> MT_TILE_BITS : 0u;
                     if (k32) {  // narrow keys: 32-bit arithmetic relative to the chunk's first key
                         const uint32_t bb = ksh0 + v * knb;
-                        uint32_t w0, w1;
-                        if (kc.saddr) { const uint32_t a = ksa + ((bb >> 5) << 2); w0 = mt_lds32(a); w1 = mt_lds32(a + 4); }
-                        else { const uint32_t* w = kwp + (bb >> 5); w0 = __ldg(w); w1 = __ldg(w + 1); }
-                        key[u] = (uint64_t)(__funnelshift_r(w0, w1, bb & 31u) & kmask) + kminv;
+                        const uint32_t* w = kwp + (bb >> 5);
+                        key[u] = (uint64_t)(__funnelshift_r(__ldg(w), __ldg(w + 1), bb & 31u) & kmask) + kminv;
                     } else {
-                        key[u] = cget(kc, kbase + cbase + v);
+                        key[u] = cget(cs[1], kbase + cbase + v);
                     }
                 }
-                if (CACHE) {
+                if (CACHE && use_cache) {
                     // hot-key front: a key that owns (or can claim) its slot is folded in shared memory
 #pragma unroll
                     for (int u = 0; u < MT_U; u++) {
                         if (!f[u]) continue;
                         if (DENSE && key[u] - dom_min >= dom_size) { f[u] = 0; continue; }
-                        const uint32_t slot = (uint32_t)((key[u] * 0x9E3779B97F4A7C15ull) >> (64 - MT_CACHE_LOG));
+                        n_probe++;
+                        const uint32_t slot = ((uint32_t)key[u] * 0x9E3779B1u) >> (32 - MT_CACHE_LOG);
                         uint64_t k = ckey[slot];
                         if (k == MT_CACHE_EMPTY) {
                             k = atomicCAS((unsigned long long*)(ckey + slot), (unsigned long long)MT_CACHE_EMPTY, (unsigned long long)key[u]);
                             if (k == MT_CACHE_EMPTY) k = key[u];
                         }
                         if (k != key[u]) continue;  // the slot belongs to another key: global table
+                        n_hit++;
                         if (NC > 0) atomicAdd(ccnt + slot, 1u);
                         if (NG > 0 && ((f[u] >> 1) & 1u)) {
                             const uint64_t v = ((const uint64_t*)(base + p.groups[0].soff_sum))[di[u]];
@@ -417,9 +332,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                         if (p.present_mode == PRESENT_BITMAP) {
                             if (f[u] && !((bitmap[b[u] >> 5] >> (b[u] & 31)) & 1u)) atomicOr(bitmap + (b[u] >> 5), 1u << (b[u] & 31));
                         } else if (p.present_mode == PRESENT_EXPLICIT) {
-                            // occurrences that contribute to a leaf whose Option flag is derived leave their trace in that flag
-                            // (k_mterms_fixup ORs it into the bucket existence): no load in their chain; the others check-and-set
-                            if (f[u] && !(p.present_from_seen && ((f[u] >> 1) & 1u)) && !p.scope.present[b[u]]) p.scope.present[b[u]] = 1;
+                            if (f[u] && !p.scope.present[b[u]]) p.scope.present[b[u]] = 1;
                         }
                     }
                 } else {
@@ -441,9 +354,11 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                             if (((f[u] >> (1 + g)) & 1u) && !G.seen[b[u]]) G.seen[b[u]] = 1;
                     } else if (G.seen_mode == SEEN_DERIVED) {  // a contribution equal to the identity leaves no trace in the
                         // cell (min / max: the smallest / largest code; f64 sum: a document whose values are all -0.0)
+                        const uint64_t* ss = (const uint64_t*)(base + (G.derive_op == MO_SUM ? G.soff_sum : G.derive_op == MO_MIN ? G.soff_min : G.soff_max));
+                        const uint64_t ident = G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull;
 #pragma unroll
                         for (int u = 0; u < MT_U; u++)
-                            if ((f[u] >> (3 + g)) & 1u) G.seen[b[u]] = 1;
+                            if (((f[u] >> (1 + g)) & 1u) && ss[di[u]] == ident) G.seen[b[u]] = 1;
                     }
                 }
 #pragma unroll
@@ -466,7 +381,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                                 if ((f[u] >> (1 + g)) & 1u) atomicAdd((unsigned long long*)(G.acc_sum + b[u]), (unsigned long long)ss[di[u]]);
                         }
                     }
-                    if (!CACHE && (G.ops & MO_MIN)) {
+                    if (G.ops & MO_MIN) {
                         const uint64_t* ss = (const uint64_t*)(base + G.soff_min);
 #pragma unroll
                         for (int u = 0; u < MT_U; u++) {
@@ -475,7 +390,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                             if (G.acc_min[b[u]] < m && __ldcg(G.acc_min + b[u]) < m) atomicMax((unsigned long long*)(G.acc_min + b[u]), (unsigned long long)m);
                         }
                     }
-                    if (!CACHE && (G.ops & MO_MAX)) {
+                    if (G.ops & MO_MAX) {
                         const uint64_t* ss = (const uint64_t*)(base + G.soff_max);
 #pragma unroll
                         for (int u = 0; u < MT_U; u++) {
@@ -487,6 +402,16 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                 }
             }
             named_bar(1 + sub, MT_SUB_THREADS);
+        }
+        if (CACHE && use_cache && ++tiles_done <= 2) {
+            n_probe = __reduce_add_sync(0xffffffffu, n_probe);
+            n_hit = __reduce_add_sync(0xffffffffu, n_hit);
+            if ((st & 31) == 0) { atomicAdd(cstat, n_probe); atomicAdd(cstat + 1, n_hit); }
+            n_probe = n_hit = 0;
+            if (tiles_done == 2) {
+                named_bar(1 + sub, MT_SUB_THREADS);
+                use_cache = cstat[1] * 16u >= cstat[0];
+            }
         }
     }
     if (CACHE) {  // flush the hot-key front: one global update per cached key and CTA
@@ -526,7 +451,6 @@ struct MFix {
     uint64_t n;
     uint8_t* present;
     const uint64_t* counts;  // non-null: present[b] = counts[b] != 0
-    const uint8_t* seen_implies_present;  // non-null: present[b] |= seen[b] (after the flags below were derived)
     int32_t n_groups;
     struct { uint64_t* cell; uint8_t* seen; uint32_t derive_op; uint32_t pad; } g[MT_MAXGROUPS];
 };
@@ -541,7 +465,6 @@ __global__ void k_mterms_fixup(const MFix x) {
                 x.g[g].seen[i] = 1;
             }
         }
-        if (x.seen_implies_present && x.seen_implies_present[i]) x.present[i] = 1;
     }
 }
 
@@ -687,65 +610,34 @@ int mterms_try(ExecState& es) {
         p.soff_koff = off; off += (MT_TILE + 1) * 4; off = (off + 15) & ~15u;
         p.soff_docof = off; off += MT_CHUNK * 2;
         p.soff_flags = off; off += MT_TILE; off = (off + 15) & ~15u;
-        p.soff_cols = off; off += 2 * MT_NCOLS * (uint32_t)sizeof(ColS);
-        p.soff_mbar = off; off += 16;
+        p.soff_cols = off; off += MT_NCOLS * (uint32_t)sizeof(ColS);
         for (int g = 0; g < p.n_groups; g++) {
             MGroup& G = p.groups[g];
             if (G.ops & MO_SUM) { G.soff_sum = off; off += MT_TILE * 8; }
             if (G.ops & MO_MIN) { G.soff_min = off; off += MT_TILE * 8; }
             if (G.ops & MO_MAX) { G.soff_max = off; off += MT_TILE * 8; }
         }
-        const uint32_t fixed_bytes = off;
-        // staged slices: sized for 1.25x the mean number of values a tile holds (+ slack), per column slot; a tile whose
-        // slice does not fit reads that column from global memory
-        uint32_t want[MT_NCOLS] = {0};
-        {
-            auto slice_bytes = [&](int slot, bool multi, bool is_vals) -> uint32_t {
-                double bits_max = 0;
-                for (auto& hs : es.hsegs) {
-                    const DevColumn& c = hs.cols[slot];
-                    if (!c.num_bits || !hs.max_doc) continue;
-                    const double per_tile = (!is_vals || !multi) ? (double)MT_TILE + 1 : 1.25 * (double)c.n_values / (double)hs.max_doc * MT_TILE + 256;
-                    bits_max = std::max(bits_max, per_tile * c.num_bits);
-                }
-                if (bits_max == 0) return 0;
-                return (uint32_t)std::min<double>(((uint64_t)(bits_max / 8) + 64 + 15) & ~15ull, 40960.0);
-            };
-            if (p.key_multi) { want[0] = slice_bytes(p.key_col, true, false); want[1] = slice_bytes(p.key_col + 1, true, true); }
-            else want[1] = slice_bytes(p.key_col, false, true);
-            for (int g = 0; g < p.n_groups; g++) {
-                const MGroup& G = p.groups[g];
-                if (G.multi) { want[2 + 2 * g] = slice_bytes(G.col, true, false); want[3 + 2 * g] = slice_bytes(G.col + 1, true, true); }
-                else want[3 + 2 * g] = slice_bytes(G.col, false, true);
-            }
-        }
+        p.sub_bytes = off;
         const size_t SMEM_MAX = 225 * 1024;
-        const bool cache = p.n_counts <= 1 && p.n_groups <= 1 && (p.n_groups == 0 || p.groups[0].ops == MO_SUM);
-        p.cache_bytes = cache ? (uint32_t)((8 + 8 + 4 + 1) << MT_CACHE_LOG) + 16 : 0;
-        p.cache_bytes = (p.cache_bytes + 15) & ~15u;
-        // the staging buffers are taken whole or not at all, largest budget first: 4 sub-blocks with staging, then 3, 2; then
-        // without staging
-        uint32_t n_sub = 0;
-        for (int staged = 1; staged >= 0 && !n_sub; staged--) {
-            uint32_t o = fixed_bytes;
-            for (int c = 0; c < MT_NCOLS; c++) {
-                p.sbuf_bytes[c] = staged ? want[c] : 0;
-                p.soff_sbuf[c] = o;
-                o += p.sbuf_bytes[c];
-            }
-            p.sub_bytes = (o + 15) & ~15u;
-            p.bitmap_bytes = 0;
-            p.present_mode = dense ? (p.n_counts > 0 ? PRESENT_COUNTS : PRESENT_EXPLICIT) : PRESENT_HASH;
-            for (uint32_t ns = MT_MAXSUB; ns >= (staged ? 2u : 1u); ns--)
-                if (p.cache_bytes + (size_t)ns * p.sub_bytes <= SMEM_MAX) { n_sub = ns; break; }
-        }
-        if (n_sub < 1) continue;
-        if (p.present_mode == PRESENT_EXPLICIT) {  // the CTA bitmap of touched buckets, when it still fits
+        p.bitmap_bytes = 0;
+        p.present_mode = dense ? (p.n_counts > 0 ? PRESENT_COUNTS : PRESENT_EXPLICIT) : PRESENT_HASH;
+        if (p.present_mode == PRESENT_EXPLICIT) {
             size_t bb = (((size_t)L.dom_size + 31) / 32) * 4;
             bb = (bb + 15) & ~(size_t)15;
-            if (bb + p.cache_bytes + (size_t)n_sub * p.sub_bytes <= SMEM_MAX) { p.bitmap_bytes = (uint32_t)bb; p.present_mode = PRESENT_BITMAP; }
+            if (bb + 2 * (size_t)p.sub_bytes <= SMEM_MAX) { p.bitmap_bytes = (uint32_t)bb; p.present_mode = PRESENT_BITMAP; }
         }
-        p.present_from_seen = p.present_mode == PRESENT_EXPLICIT && p.n_groups >= 1 && p.groups[0].seen_mode == SEEN_DERIVED ? 1u : 0u;
+        // the hot-key front: shapes with at most one count and one sum-only leaf group, when it costs no sub-block
+        bool cache = p.n_counts <= 1 && p.n_groups <= 1 && (p.n_groups == 0 || p.groups[0].ops == MO_SUM);
+        p.cache_bytes = 0;
+        if (cache) {
+            const uint32_t cb = ((uint32_t)((8 + 8 + 4 + 1) << MT_CACHE_LOG) + 8 * MT_MAXSUB + 15) & ~15u;
+            const size_t without = std::min<size_t>(MT_MAXSUB, (SMEM_MAX - p.bitmap_bytes) / p.sub_bytes);
+            const size_t with = p.bitmap_bytes + cb < SMEM_MAX ? std::min<size_t>(MT_MAXSUB, (SMEM_MAX - p.bitmap_bytes - cb) / p.sub_bytes) : 0;
+            static const bool no_cache = getenv("TAGG_MT_NOCACHE") != nullptr;  // experiment switch
+            if (with >= 1 && with == without && !no_cache) p.cache_bytes = cb; else cache = false;
+        }
+        uint32_t n_sub = (uint32_t)std::min<size_t>(MT_MAXSUB, (SMEM_MAX - p.bitmap_bytes - p.cache_bytes) / p.sub_bytes);
+        if (n_sub < 1) continue;
         const size_t smem_bytes = p.bitmap_bytes + p.cache_bytes + (size_t)n_sub * p.sub_bytes;
         mterms_fn fn = dense ? pick_ng<true>(p.n_groups, p.n_counts, cache) : pick_ng<false>(p.n_groups, p.n_counts, cache);
         {
@@ -804,7 +696,6 @@ int mterms_try(ExecState& es) {
             memset(&fx, 0, sizeof(fx));
             fx.n = n_cells;
             if (p.present_mode == PRESENT_COUNTS) { fx.present = es.arena + L.off_present; fx.counts = p.count_acc[0]; }
-            if (p.present_from_seen) { fx.present = es.arena + L.off_present; fx.seen_implies_present = p.groups[0].seen; }
             for (int g = 0; g < p.n_groups; g++) {
                 const MGroup& G = p.groups[g];
                 if (G.seen_mode != SEEN_DERIVED) continue;
@@ -813,7 +704,7 @@ int mterms_try(ExecState& es) {
                 d.seen = G.seen;
                 d.derive_op = G.derive_op;
             }
-            if (fx.counts || fx.n_groups || fx.seen_implies_present) {
+            if (fx.counts || fx.n_groups) {
                 k_mterms_fixup<<<aux_grid, 256, 0, es.st>>>(fx);
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_mterms_fixup launch failed: %s", cudaGetErrorString(e));
