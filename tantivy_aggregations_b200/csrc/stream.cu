@@ -518,7 +518,11 @@ static int stream_launch(ExecState& es, bool first_launch) {
             const uint32_t bits = span ? 64 - (uint32_t)__builtin_clzll(span) : 0;
             sp.nib_lo = glo;
             sp.nib_shift = bits > 4 ? bits - 4 : 0;
-            if (table_bytes == 0) table_bytes = 128;
+            sp.nib_hi32 = sp.nib_shift >= 32 ? 1u : 0u;
+            // the level bytes also record which buckets exist: they replace the CTA bitmap
+            sp.present_from_nib = sp.soff_present_bits ? 1u : 0u;
+            sp.soff_present_bits = 0;
+            table_bytes = 128;
             sp.soff_nib = (uint32_t)table_bytes;
             table_bytes += ((size_t)sp.dom_size + 127) & ~(size_t)127;
             nib = true;
@@ -530,7 +534,13 @@ static int stream_launch(ExecState& es, bool first_launch) {
         bool ok = false;
         for (auto& c : cand)
             if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
-        if (!ok) { nib = false; sp.soff_nib = 0; table_bytes = sp.soff_present_bits ? 128 + ((((size_t)sp.dom_size + 31) / 32 * 4 + 127) & ~(size_t)127) : 0; }
+        if (!ok) {  // no room for the level bytes: back to the bitmap alone
+            nib = false;
+            sp.soff_nib = 0;
+            if (sp.present_from_nib) sp.soff_present_bits = 128;
+            sp.present_from_nib = 0;
+            table_bytes = sp.soff_present_bits ? 128 + ((((size_t)sp.dom_size + 31) / 32 * 4 + 127) & ~(size_t)127) : 0;
+        }
     }
     if (stab) {
         // more consumer warps beat a deeper ring (measured on C3: 3 groups x 2 stages 2.08 ms, 2 x 3 2.58 ms)

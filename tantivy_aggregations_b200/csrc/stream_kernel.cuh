@@ -104,6 +104,11 @@ struct SParams {
     // fire-and-forget RED); updates of the byte are plain stores (a lost update only weakens the filter)
     uint32_t soff_nib, nib_shift;
     uint64_t nib_lo;
+    // nib_hi32: the span is wide enough that the level can be taken from the high word alone, (code_hi - nib_lo_hi) >>
+    // (nib_shift - 32) — any monotone function of the code is a valid filter level.  present_from_nib: both nibbles of a
+    // touched bucket's byte are raised (level + (15 - level) == 15, never both zero), so the byte doubles as the bucket-
+    // existence record and the CTA bitmap is not needed
+    uint32_t nib_hi32, present_from_nib;
     uint32_t soff_present_bits;  // global tables without a count: CTA bitmap of touched buckets (0 = none), flushed at the end
     uint8_t* present;      // maintained by the kernel (global tables without a count); nullptr otherwise
     uint8_t* present_out;  // STAB: written by the final table merge
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 if (p.soff_present_bits) {  // no count names the bucket: CTA bitmap, flushed once at the end
                                     const uint32_t wa = smem_saddr + p.soff_present_bits + 4 * (rel[u] >> 5), bit = 1u << (rel[u] & 31);
                                     if (!(lds32(wa) & bit)) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(bit) : "memory");
-                                } else if (p.present && !p.present[rel[u]]) {
+                                } else if (!p.present_from_nib && p.present && !p.present[rel[u]]) {
                                     p.present[rel[u]] = 1;
                                 }
                             }
@@ -700,8 +705,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 code[u] = BUCKET == BK_RANK ? tail_code[u] : tget(bc[g], dl[u]);
                                 if (nibf) {
                                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(nfb[u]) : "r"(smem_saddr + p.soff_nib + rel[u]));
-                                    const uint64_t lv = code[u] >= p.nib_lo ? (code[u] - p.nib_lo) >> p.nib_shift : 0ull;
-                                    nq[u] = lv > 15 ? 15u : (uint32_t)lv;
+                                    if (p.nib_hi32) {
+                                        nq[u] = min(((uint32_t)(code[u] >> 32) - (uint32_t)(p.nib_lo >> 32)) >> (p.nib_shift - 32), 15u);
+                                    } else {
+                                        const uint64_t lv = code[u] >= p.nib_lo ? (code[u] - p.nib_lo) >> p.nib_shift : 0ull;
+                                        nq[u] = lv > 15 ? 15u : (uint32_t)lv;
+                                    }
                                 } else if (filt) {  // cur_* hold the filter word; code[u] is compared through its own rank word below
                                     if (ops & OPB_MIN) cur_min[u] = lds32(smem_saddr + p.soff_tab_min[g] + 4 * rel[u]);
                                     if (ops & OPB_MAX) cur_max[u] = lds32(smem_saddr + p.soff_tab_max[g] + 4 * rel[u]);
@@ -721,10 +730,11 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 }
                                 if (nibf) {
                                     const uint32_t fx = nfb[u] >> 4, fn = nfb[u] & 15u, qx = nq[u], qn = 15u - nq[u];
-                                    uint32_t nx = fx, nn = fn;
-                                    if ((ops & OPB_MAX) && qx >= fx) { atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]); nx = qx; }
-                                    if ((ops & OPB_MIN) && qn >= fn) { atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]); nn = qn; }
-                                    if (nx != fx || nn != fn) asm volatile("st.shared.u8 [%0], %1;" ::"r"(smem_saddr + p.soff_nib + rel[u]), "r"((nx << 4) | nn) : "memory");
+                                    if ((ops & OPB_MAX) && qx >= fx) atomicMax((unsigned long long*)(G.acc_max + rel[u]), (unsigned long long)code[u]);
+                                    if ((ops & OPB_MIN) && qn >= fn) atomicMax((unsigned long long*)(G.acc_min + rel[u]), (unsigned long long)~code[u]);
+                                    // (both nibbles are raised whatever the ops: the byte is also the bucket's existence record)
+                                    const uint32_t nb8 = (max(fx, qx) << 4) | max(fn, qn);
+                                    if (nb8 != nfb[u]) asm volatile("st.shared.u8 [%0], %1;" ::"r"(smem_saddr + p.soff_nib + rel[u]), "r"(nb8) : "memory");
                                     continue;
                                 }
                                 if (filt) {  // fire-and-forget: no load sits between the filter and the global RED
@@ -930,6 +940,12 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         }
     }
 
+    if (!STAB && BUCKET == BK_TERMS && p.present_from_nib) {  // a touched bucket's level byte is never zero
+        __syncthreads();
+        const uint8_t* nb = smem + p.soff_nib;
+        for (uint32_t i = tid; i < (uint32_t)p.dom_size; i += blockDim.x)
+            if (nb[i]) p.present_out[i] = 1;
+    }
     if (!STAB && BUCKET == BK_TERMS && p.soff_present_bits) {
         __syncthreads();
         const uint32_t* bm = (const uint32_t*)(smem + p.soff_present_bits);

@@ -33,6 +33,20 @@ if "c1" in which:
 if "c1x" in which:
     segs = segs_of(1_000_000_000, 64, [price]); run("C1 x1000 (1G docs)", ta.Searcher(ctx, segs), ta.AllQuery(), c1agg)
     for s in segs: s.close()
+if "c2" in which:
+    segs = segs_of(100_000_000, 8, [lambda s, b: s.synth_column(STATUS, ta.U64, 1, SEED, 11, b, 0, 4),
+                                    lambda s, b: s.synth_column(CATEGORY, ta.U64, 1, SEED, 22, b, 1, 10_000), price])
+    S = ta.Searcher(ctx, segs)
+    fq = ta.CachedQuery(ta.TermQuery(STATUS, ta.U64, 0), segs)
+    run("C2 filter(status=0,(count,terms(cat 10k,(count,min)))) 100M", S, ta.AllQuery(),
+        lambda: ta.filter_agg(fq, (ta.count_agg(), ta.terms_agg_u64(CATEGORY, (ta.count_agg(), ta.min_agg_f64(PRICE))))))
+    for s in segs: s.close()
+if "c3hist" in which:
+    segs = segs_of(500_000_000, 8, [price]); S = ta.Searcher(ctx, segs)
+    rng = np.random.default_rng(3)
+    q = ta.CachedQuery(ta.BitsetQuery({i: rng.integers(0, 256, size=(s.max_doc + 7) // 8, dtype=np.uint8) for i, s in enumerate(segs)}), segs)
+    run("C3 hist(price,0,10,count) 500M/50%", S, q, lambda: ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()))
+    for s in segs: s.close()
 if "c3pair" in which:  # only the fused (histogram, percentiles) tuple — the ncu target
     segs = segs_of(500_000_000, 8, [price]); S = ta.Searcher(ctx, segs)
     rng = np.random.default_rng(3)
