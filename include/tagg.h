@@ -209,6 +209,14 @@ int tagg_plan_set_readout(tagg_plan* plan, int readout);
 int tagg_execute(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs,
                  tagg_result** out);
 int tagg_result_free(tagg_result* res);
+/* The same call split at its one synchronisation point, so that a host can keep two (or more) queries in flight — the
+ * preparation of query i+1 then overlaps the kernels of query i (the reference overlaps segments on its thread pool,
+ * searcher.rs:79-92; here the unit in flight is the whole query).  tagg_execute_begin returns as soon as the pass, the
+ * compaction and the download are queued; host buffers handed in (docsets) stay borrowed until tagg_pending_wait returns,
+ * which always consumes the pending handle. */
+typedef struct tagg_pending tagg_pending;
+int tagg_execute_begin(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_pending** out);
+int tagg_pending_wait(tagg_pending* pending, tagg_result** out);
 /* PreparedAgg::merge (count.rs:39-41, sum.rs:59-70, minmax.rs:59-72, terms.rs:85-92,
  * histogram.rs:90-97); both results must come from the same plan. */
 int tagg_result_merge(tagg_result* dst, const tagg_result* src);

@@ -54,6 +54,7 @@ pub const TAGG_READOUT_LAZY: c_int = 1;
 #[repr(C)] pub struct tagg_segment { _p: [u8; 0] }
 #[repr(C)] pub struct tagg_plan { _p: [u8; 0] }
 #[repr(C)] pub struct tagg_result { _p: [u8; 0] }
+#[repr(C)] pub struct tagg_pending { _p: [u8; 0] }
 
 /// One node of the flattened aggregation tree, pre-order (48 bytes, `struct tagg_node`).
 #[repr(C)]
@@ -141,6 +142,8 @@ extern "C" {
     // ---- execution
     pub fn tagg_execute(plan: *const tagg_plan, inputs: *const tagg_segment_input, n_inputs: u32, out: *mut *mut tagg_result) -> c_int;
     pub fn tagg_result_free(res: *mut tagg_result) -> c_int;
+    pub fn tagg_execute_begin(plan: *const tagg_plan, inputs: *const tagg_segment_input, n_inputs: u32, out: *mut *mut tagg_pending) -> c_int;
+    pub fn tagg_pending_wait(pending: *mut tagg_pending, out: *mut *mut tagg_result) -> c_int;
     pub fn tagg_result_merge(dst: *mut tagg_result, src: *const tagg_result) -> c_int;
     // ---- multi-GPU
     pub fn tagg_comm_unique_id(out: *mut u8) -> c_int;

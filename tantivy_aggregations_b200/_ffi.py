@@ -88,6 +88,8 @@ SYMBOLS = {
     "tagg_plan_destroy": (C.c_int, [_P]),
     "tagg_execute": (C.c_int, [_P, C.POINTER(SegmentInput), C.c_uint32, _PP]),
     "tagg_result_free": (C.c_int, [_P]),
+    "tagg_execute_begin": (C.c_int, [_P, C.POINTER(SegmentInput), C.c_uint32, _PP]),
+    "tagg_pending_wait": (C.c_int, [_P, _PP]),
     "tagg_result_merge": (C.c_int, [_P, _P]),
     "tagg_comm_unique_id": (C.c_int, [_P]),
     "tagg_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),

@@ -57,6 +57,7 @@ CallRes* tagg_ctx::acquire_call() {
     cudaEventCreate(&c->ev1);
     for (auto& e : c->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->chain_ev, cudaEventDisableTiming);
     c->pinned_bytes = 8 << 20;  // arenas up to this size come back whole in one pinned copy
     if (cudaHostAlloc((void**)&c->pinned, c->pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
         c->pinned = nullptr;
@@ -229,10 +230,12 @@ int tagg_ctx_destroy(tagg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     tagg_comm_destroy(ctx);
     for (auto c : ctx->call_pool) {
+        for (auto& b : c->blocks) cudaFree(b.p);
         cudaStreamDestroy(c->st);
         cudaStreamDestroy(c->st2);
         for (auto e : c->chunk_ev) cudaEventDestroy(e);
         cudaEventDestroy(c->join_ev);
+        cudaEventDestroy(c->chain_ev);
         cudaEventDestroy(c->ev0);
         cudaEventDestroy(c->ev1);
         if (c->pinned) cudaFreeHost(c->pinned);
@@ -353,6 +356,12 @@ int tagg_plan_destroy(tagg_plan* plan) {
 int tagg_execute(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_result** out) {
     return exec_run(plan, inputs, n_inputs, 0, -1, out);
 }
+
+int tagg_execute_begin(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_pending** out) {
+    return exec_begin(plan, inputs, n_inputs, out);
+}
+
+int tagg_pending_wait(tagg_pending* pending, tagg_result** out) { return exec_wait(pending, out); }
 
 int tagg_execute_collective(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_result** out) {
     return exec_run(plan, inputs, n_inputs, 1, -1, out);

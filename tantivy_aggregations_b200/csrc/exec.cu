@@ -31,15 +31,45 @@ const void* ExecState::pin(const void* src, size_t bytes) {
     call->pinned_used = at + bytes;
     return call->pinned + at;
 }
+void* ExecState::cache_alloc(size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    CallRes::DevBlock* best = nullptr;
+    for (auto& b : call->blocks)
+        if (!b.in_use && b.bytes >= bytes && b.bytes <= std::max<size_t>(2 * bytes, bytes + (1u << 20)) && (!best || b.bytes < best->bytes)) best = &b;
+    if (!best) {
+        if (call->blocks.size() >= 48) {  // keep the cache small: drop what is not in use
+            std::vector<CallRes::DevBlock> keep;
+            for (auto& b : call->blocks) { if (b.in_use) keep.push_back(b); else cudaFreeAsync(b.p, st); }
+            call->blocks.swap(keep);
+        }
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        call->blocks.push_back({p, bytes, false});
+        best = &call->blocks.back();
+    }
+    best->in_use = true;
+    cached.push_back(best->p);
+    return best->p;
+}
+void ExecState::cache_release(void* p) {
+    if (!p) return;
+    for (auto& b : call->blocks)
+        if (b.p == p) { b.in_use = false; break; }
+    cached.erase(std::remove(cached.begin(), cached.end(), p), cached.end());
+}
 void ExecState::free_temps() {
     pct_rank_release(*this);
     compact_release(*this);
     for (void* p : temps) cudaFreeAsync(p, st);
     temps.clear();
-    if (arena) cudaFreeAsync(arena, st);
     arena = nullptr;
-    if (d_plan) cudaFreeAsync(d_plan, st);
     d_plan = nullptr;
+    if (call) {
+        for (void* p : cached)
+            for (auto& b : call->blocks)
+                if (b.p == p) { b.in_use = false; break; }
+    }
+    cached.clear();
     for (int i = 0; i < 4; i++) {
         if (pct_codes[i]) cudaFreeAsync(pct_codes[i], st);
         if (pct_buckets[i]) cudaFreeAsync(pct_buckets[i], st);
@@ -61,9 +91,8 @@ static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 template <typename T>
 static int dev_alloc(ExecState& es, T** out, size_t bytes) {
-    void* p = nullptr;
-    CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, es.st));
-    es.temps.push_back(p);
+    void* p = es.cache_alloc(bytes);
+    if (!p) return tagg_fail(TAGG_ERR_OOM, "device scratch allocation failed (%zu bytes)", bytes);
     *out = (T*)p;
     return 0;
 }
@@ -234,9 +263,8 @@ static int resolve_segments(ExecState& es, const tagg_segment_input* inputs, uin
                     if (inputs[i].filters[f].kind == TAGG_DOCSET_BITSET) total += take;
             }
             if (total) {
-                void* blk = nullptr;
-                CUDA_TRY(cudaMallocAsync(&blk, total, es.st));
-                es.temps.push_back(blk);
+                void* blk = es.cache_alloc(total);
+                if (!blk) return tagg_fail(TAGG_ERR_OOM, "docset staging allocation failed (%zu bytes)", total);
                 CUDA_TRY(cudaMemsetAsync(blk, 0, total, es.st));
                 es.ds_block = (uint8_t*)blk;
                 es.ds_bytes = total;
@@ -470,8 +498,8 @@ static int layout_arena(ExecState& es) {
         }
     }
     es.arena_bytes = off;
-    void* p = nullptr;
-    CUDA_TRY(cudaMallocAsync(&p, es.arena_bytes, es.st));
+    void* p = es.cache_alloc(es.arena_bytes);
+    if (!p) return tagg_fail(TAGG_ERR_OOM, "accumulator arena allocation failed (%zu bytes)", es.arena_bytes);
     es.arena = (uint8_t*)p;
     CUDA_TRY(cudaMemsetAsync(es.arena, 0, es.arena_bytes, es.st));
     // f64 sum cells start at -0.0: x + -0.0 == x for every x, so the first value "replaces" (sum.rs:95-102) and a sum
@@ -604,8 +632,8 @@ static int build_dev_plan(ExecState& es) {
         P.pct_count[k] = es.pct_count[k];
         P.pct_cap[k] = es.pct_cap[k];
     }
-    void* p = nullptr;
-    CUDA_TRY(cudaMallocAsync(&p, sizeof(DevPlan), es.st));
+    void* p = es.cache_alloc(sizeof(DevPlan));
+    if (!p) return tagg_fail(TAGG_ERR_OOM, "plan allocation failed");
     es.d_plan = (DevPlan*)p;
     CUDA_TRY(cudaMemcpyAsync(es.d_plan, es.pin(&P, sizeof(DevPlan)), sizeof(DevPlan), cudaMemcpyHostToDevice, es.st));
     return 0;
@@ -613,60 +641,38 @@ static int build_dev_plan(ExecState& es) {
 
 // One call of the hot path.  mode: 0 = this GPU only (tagg_execute), 1 = collective, every rank receives the merged fruit
 // (tagg_execute_collective), 2 = collective, merged on `root` only (tagg_execute_reduce).
-int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int mode, int root,
-             tagg_result** out) {
-    if (!plan || !out || (n_inputs && !inputs)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_execute: null argument");
-    tagg_ctx* ctx = plan->ctx;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    const bool collective = mode != 0;
-    if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "collective execution needs tagg_comm_init first");
-    if (mode == 2 && (root < 0 || root >= ctx->n_ranks)) return tagg_fail(TAGG_ERR_BAD_ARG, "root rank %d out of range", root);
+//
+// The call is split at its ONE synchronisation point: begin() resolves the inputs, lays the arena out, launches the pass,
+// the cross-GPU merge, the compaction and the download, and returns without waiting; finish() waits, checks the flags,
+// redoes the pass in the rare cases that need it (hash table growth, percentile bins that failed their precision check,
+// an ambiguous signed zero, a key-domain agreement that moved) and hands the fruit out.  tagg_execute = begin + finish;
+// tagg_execute_begin / tagg_pending_wait let a host keep two queries in flight (each on its own stream and pinned block),
+// so that the host-side preparation of query i+1 overlaps the kernels of query i.
+struct ExecCall {
+    ExecState es;
+    const tagg_plan* plan = nullptr;
+    tagg_ctx* ctx = nullptr;
+    uint32_t n_inputs = 0;
+    int mode = 0, root = -1;
+    bool collective = false;
+    bool edge_straddle = false, edge_nan = false;
+    std::vector<uint64_t> agreed, dom_used;
+    bool agree_pending = false;
+    float ms_total = 0;
+    tagg_result* res = nullptr;
+    bool arena_merge = false, i_read = true, ok = false;
+    uint32_t* flags = nullptr;
+    uint32_t flags_local[4] = {0, 0, 0, 0};
+    int attempt = 0;
+    std::chrono::steady_clock::time_point t_begin;
 
-    static const bool trace = getenv("TAGG_TRACE") != nullptr;
-    auto t_begin = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
+    void lap(const char* what) {
+        static const bool trace = getenv("TAGG_TRACE") != nullptr;
         if (!trace) return;
         auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[tagg] %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_begin).count());
-    };
-    ExecState es;
-    es.ctx = ctx;
-    es.plan = plan;
-    es.meta = plan->meta.get();
-    es.collective = collective;
-    es.call = ctx->acquire_call();
-    es.st = es.call->st;
-    es.ev0 = es.call->ev0;
-    es.ev1 = es.call->ev1;
-
-    lap("acquire");
-    int rc = resolve_segments(es, inputs, n_inputs);
-    if (rc) return rc;
-    lap("resolve_segments");
-    if (n_inputs) {
-        rc = dev_alloc(es, &es.d_segs, sizeof(DevSegment) * n_inputs);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.pin(es.hsegs.data(), sizeof(DevSegment) * n_inputs), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
     }
-
-    rc = issue_uploads(es);
-    if (rc) return rc;
-    // f64 MIN / MAX: the order of the codes is the reference's PartialOrd fold except around NaN and the two zeros
-    bool edge_straddle = false, edge_nan = false;
-    edge_scan(es, &edge_straddle, &edge_nan);
-    es.edge_exact = edge_nan;  // a NaN in a column: exact path right away; zeros: only if the result turns out ambiguous
-
-    // Collective: every rank lays its tables out over the SAME key domains, agreed with one tiny min all-reduce per call
-    // (comm.cu).  The agreed vector of the previous call on the same (plan, segment set) is used OPTIMISTICALLY: the pass
-    // starts at once on it while the all-reduce is in flight, and is redone in the rare case the agreement moved (some
-    // rank's segments changed).  Every rank issues exactly one agreement per call, so the NCCL call sequences always match.
-    std::vector<uint64_t> agreed;     // this call's agreement, once it is in
-    bool agree_pending = false;
-    std::vector<uint64_t> dom_used;   // the vector the current pass was laid out with
-
-    float ms_total = 0;
-    tagg_result* res = nullptr;
-    auto take_result = [&]() {
+    void take_result() {
         {
             std::lock_guard<std::mutex> g(ctx->mu);
             if (!ctx->result_pool.empty()) { res = ctx->result_pool.back(); ctx->result_pool.pop_back(); }
@@ -679,8 +685,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         res->merged_elsewhere = 0;
         res->d_stream = es.st;
         res->pcts.clear();
-    };
-    auto drop_result = [&]() {
+    }
+    void drop_result() {
         if (!res) return;
         res->release_device();
         res->meta.reset();
@@ -688,12 +694,56 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         std::lock_guard<std::mutex> g(ctx->mu);
         if (ctx->result_pool.size() < 4) ctx->result_pool.push_back(res); else delete res;
         res = nullptr;
-    };
-    bool ok = false;
-    struct Guard { std::function<void()> f; ~Guard() { f(); } } guard{[&]() { if (!ok) drop_result(); }};
+    }
+    ~ExecCall() { if (!ok) drop_result(); }
 
-    bool arena_merge = false;
-    for (int attempt = 0;; attempt++) {
+    int begin(const tagg_plan* plan_, const tagg_segment_input* inputs, uint32_t n_inputs_, int mode_, int root_);
+    int issue();                // one attempt, up to (not including) the synchronisation
+    int complete(bool* redo);   // the synchronisation and everything behind it
+    int finish(tagg_result** out);
+};
+
+int ExecCall::begin(const tagg_plan* plan_, const tagg_segment_input* inputs, uint32_t n_inputs_, int mode_, int root_) {
+    plan = plan_; n_inputs = n_inputs_; mode = mode_; root = root_;
+    ctx = plan->ctx;
+    t_begin = std::chrono::steady_clock::now();
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    collective = mode != 0;
+    if (collective && !ctx->nccl) return tagg_fail(TAGG_ERR_NCCL, "collective execution needs tagg_comm_init first");
+    if (mode == 2 && (root < 0 || root >= ctx->n_ranks)) return tagg_fail(TAGG_ERR_BAD_ARG, "root rank %d out of range", root);
+    es.ctx = ctx;
+    es.plan = plan;
+    es.meta = plan->meta.get();
+    es.collective = collective;
+    es.call = ctx->acquire_call();
+    es.st = es.call->st;
+    es.ev0 = es.call->ev0;
+    es.ev1 = es.call->ev1;
+    lap("acquire");
+    int rc = resolve_segments(es, inputs, n_inputs);
+    if (rc) return rc;
+    lap("resolve_segments");
+    if (n_inputs) {
+        rc = dev_alloc(es, &es.d_segs, sizeof(DevSegment) * n_inputs);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(es.d_segs, es.pin(es.hsegs.data(), sizeof(DevSegment) * n_inputs), sizeof(DevSegment) * n_inputs, cudaMemcpyHostToDevice, es.st));
+    }
+    rc = issue_uploads(es);
+    if (rc) return rc;
+    // f64 MIN / MAX: the order of the codes is the reference's PartialOrd fold except around NaN and the two zeros
+    edge_scan(es, &edge_straddle, &edge_nan);
+    es.edge_exact = edge_nan;  // a NaN in a column: exact path right away; zeros: only if the result turns out ambiguous
+    attempt = 0;
+    return issue();
+}
+
+// Collective: every rank lays its tables out over the SAME key domains, agreed with one tiny min all-reduce per call
+// (comm.cu).  The agreed vector of the previous call on the same (plan, segment set) is used OPTIMISTICALLY: the pass
+// starts at once on it while the all-reduce is in flight, and is redone in the rare case the agreement moved (some
+// rank's segments changed).  Every rank issues exactly one agreement per call, so the NCCL call sequences always match.
+int ExecCall::issue() {
+    int rc = 0;
+    for (;; attempt++) {
         std::vector<uint64_t> dom, bounds;
         rc = scope_domains_local(es, dom, bounds);
         if (rc) return rc;
@@ -731,15 +781,23 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         if (rc) return rc;
         lap("layout");
 
+        {
+            cudaEvent_t prev = nullptr;
+            {
+                std::lock_guard<std::mutex> g(ctx->mu);
+                prev = ctx->last_pass_done;
+            }
+            if (prev && prev != es.call->chain_ev) CUDA_TRY(cudaStreamWaitEvent(es.st, prev, 0));
+        }
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
         es.skip.assign(es.meta->nodes.size(), 0);
         const bool fast_ok = ctx->path != 1 && !es.edge_exact;
         if (es.edge_exact && ctx->path == 2)
-            return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over NaN or signed zeros runs on the exact (generic) path; path is forced to stream");
+            return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over NaN or signed zeros runs on the exact (generic) path; path is forced to stream");
         int handled = 0;
         if (fast_ok) {
             handled = stream_try(es);
-            if (handled < 0) return rc = -handled;
+            if (handled < 0) return -handled;
         }
         // a rank-bin pass that was planned but whose launch did not happen (its member is not flagged) must not shadow
         // the exact path
@@ -752,12 +810,12 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         int mt = 0;
         if (handled != 1 && fast_ok) {  // K5: terms keyed by multi-valued / hashed fields
             mt = mterms_try(es);
-            if (mt < 0) return rc = -mt;
+            if (mt < 0) return -mt;
             if (mt > 0 && plan_fully_covered(es)) handled = 1;
             else if (mt > 0) handled = 2;
         }
         if (handled != 1) {
-            if (ctx->path == 2) return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
+            if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "the plan has no streaming fast shape (path forced to stream)");
             es.path_used = mt > 0 ? 5 : handled == 2 ? 3 : 1;
             rc = alloc_percentile_buffers(es);
             if (rc) return rc;
@@ -797,8 +855,8 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
                 }
                 CUDA_TRY(cudaStreamSynchronize(es.st));
                 pct_rank_release(es);
-                cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
-                if (es.d_plan) cudaFreeAsync(es.d_plan, es.st);
+                es.cache_release(es.arena); es.arena = nullptr;
+                es.cache_release(es.d_plan);
                 es.d_plan = nullptr;
                 continue;
             }
@@ -808,112 +866,136 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
         // zero order is per rank) as compact results, after it
         arena_merge = collective && es.meta->pct_node.empty() && !es.edge_exact;
         for (auto& L : es.scopes) arena_merge = arena_merge && L.mode == SCOPE_DENSE;
-        const bool i_read = !(arena_merge && mode == 2 && ctx->rank != root);
+        i_read = !(arena_merge && mode == 2 && ctx->rank != root);
         if (arena_merge) {
             rc = comm_merge_arena(es, mode == 2 ? root : -1);
             if (rc) return rc;
         }
         rc = pct_rank_prefetch(es);
         if (rc) return rc;
-        uint32_t* flags = (uint32_t*)const_cast<void*>(es.pin(nullptr, 16));  // [overflow][bad ids]
-        uint32_t flags_local[4] = {0, 0, 0, 0};
+        flags = (uint32_t*)const_cast<void*>(es.pin(nullptr, 16));  // [overflow][bad ids]
         if (!flags) flags = flags_local;
         flags[0] = flags[1] = 0;
         take_result();
         if (i_read) {
             rc = compact_launch(es);
             if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(es.call->chain_ev, es.st));
+        {
+            std::lock_guard<std::mutex> g(ctx->mu);
+            ctx->last_pass_done = es.call->chain_ev;
+        }
+        if (i_read) {
             rc = compact_download_begin(es, res);
             if (rc) return rc;
         }
         CUDA_TRY(cudaMemcpyAsync(&flags[0], es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
         if (es.d_bad_ids) CUDA_TRY(cudaMemcpyAsync(&flags[1], es.d_bad_ids, 4, cudaMemcpyDeviceToHost, es.st));
-        CUDA_TRY(cudaStreamSynchronize(es.st));
-        lap("synced");
-        const uint32_t overflow0 = flags[0];
-        if (flags[1]) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id filter docset holds ids that are not strictly ascending or >= max_doc of its segment");
-        float ms = 0;
-        cudaEventElapsedTime(&ms, es.ev0, es.ev1);
-        ms_total += ms;
-        uint32_t overflow = overflow0;
-        bool redo = overflow != 0;
-        if (!overflow) {
-            for (int k = 0; k < 4 && !redo; k++)
-                if (es.rank[k].active) {
-                    const int pr = pct_rank_collect(es, k);
-                    if (pr < 0) return rc = -pr;
-                    if (pr == 0) { redo = true; overflow = 3; }
-                }
-        }
-        if (!redo) {
-            if (i_read) {
-                rc = compact_finish(es, res);
-                if (rc) return rc;
-                rc = read_percentiles(es, res);
-                if (rc) return rc;
-            } else {
-                res->merged_elsewhere = 1;
-                res->n_scope.assign(es.scopes.size(), 0);
-                res->off_keys.assign(es.scopes.size(), 0); res->off_parents.assign(es.scopes.size(), 0);
-                res->off_values.assign(es.slots.size(), 0); res->off_seen.assign(es.slots.size(), 0);
-                int r2 = 0;
-                if (!res->img) { res->img = (uint8_t*)malloc(64); res->img_cap = 64; res->img_pinned = false; if (!res->img) r2 = 1; }
-                if (r2) return rc = tagg_fail(TAGG_ERR_OOM, "out of memory");
-                res->has_img = true;
-                res->pcts.resize(es.meta->pct_node.size());
+        return 0;
+    }
+}
+
+int ExecCall::complete(bool* redo_out) {
+    int rc = 0;
+    *redo_out = false;
+    CUDA_TRY(cudaStreamSynchronize(es.st));
+    lap("synced");
+    if (flags[1]) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id filter docset holds ids that are not strictly ascending or >= max_doc of its segment");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, es.ev0, es.ev1);
+    ms_total += ms;
+    uint32_t overflow = flags[0];
+    bool redo = overflow != 0;
+    if (!overflow) {
+        for (int k = 0; k < 4 && !redo; k++)
+            if (es.rank[k].active) {
+                const int pr = pct_rank_collect(es, k);
+                if (pr < 0) return -pr;
+                if (pr == 0) { redo = true; overflow = 3; }
             }
-            // a column that spans both zeros: the order of the codes picked -0.0 as the minimum (+0.0 as the maximum); if
-            // the other zero was collected too the reference keeps whichever came FIRST (minmax.rs:99-102) — exact path
-            if (!es.edge_exact && edge_straddle && !collective) {
-                rc = result_ensure_host(res);
-                if (rc) return rc;
-                bool ambiguous = false;
-                for (size_t k = 0; k < es.slot_edge.size() && !ambiguous; k++) {
-                    if (es.slot_edge[k] != 1) continue;
-                    const uint64_t amb = es.meta->nodes[es.meta->slot_node[k]].op == TAGG_OP_MIN ? F64_NEG_ZERO_BITS : 0ull;
-                    const uint64_t n = res->slot_len(k);
-                    const uint64_t* V = res->slot_values(k);
-                    const uint8_t* Sn = res->slot_seen(k);
-                    for (size_t i = 0; i < n && !ambiguous; i++) ambiguous = Sn[i] && V[i] == amb;
-                }
-                if (ambiguous) {
-                    if (ctx->path == 2) return rc = tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over both signed zeros runs on the exact (generic) path; path is forced to stream");
-                    es.edge_exact = true;
-                    redo = true;
-                }
-            }
-            if (!redo) break;
+    }
+    if (!redo) {
+        if (i_read) {
+            rc = compact_finish(es, res);
+            if (rc) return rc;
+            rc = read_percentiles(es, res);
+            if (rc) return rc;
+        } else {
+            res->merged_elsewhere = 1;
+            res->n_scope.assign(es.scopes.size(), 0);
+            res->off_keys.assign(es.scopes.size(), 0); res->off_parents.assign(es.scopes.size(), 0);
+            res->off_values.assign(es.slots.size(), 0); res->off_seen.assign(es.slots.size(), 0);
+            if (!res->img) { res->img = (uint8_t*)malloc(64); res->img_cap = 64; res->img_pinned = false; }
+            if (!res->img) return tagg_fail(TAGG_ERR_OOM, "out of memory");
+            res->has_img = true;
+            res->pcts.resize(es.meta->pct_node.size());
         }
-        drop_result();
-        if (overflow == 3) {  // the rank bins could not resolve this distribution
-            bool cached = false;
-            for (int k = 0; k < 4; k++) cached = cached || (es.rank[k].active && es.rank[k].from_cache);
-            if (cached) {  // ... with thresholds remembered from another docset: sample this one afresh
-                std::lock_guard<std::mutex> g(plan->mu);
-                for (auto& pc : plan->pct_cache) pc.valid = false;
-            } else {
-                es.no_rank = true;  // exact path
+        // a column that spans both zeros: the order of the codes picked -0.0 as the minimum (+0.0 as the maximum); if
+        // the other zero was collected too the reference keeps whichever came FIRST (minmax.rs:99-102) — exact path
+        if (!es.edge_exact && edge_straddle && !collective) {
+            rc = result_ensure_host(res);
+            if (rc) return rc;
+            bool ambiguous = false;
+            for (size_t k = 0; k < es.slot_edge.size() && !ambiguous; k++) {
+                if (es.slot_edge[k] != 1) continue;
+                const uint64_t amb = es.meta->nodes[es.meta->slot_node[k]].op == TAGG_OP_MIN ? F64_NEG_ZERO_BITS : 0ull;
+                const uint64_t n = res->slot_len(k);
+                const uint64_t* V = res->slot_values(k);
+                const uint8_t* Sn = res->slot_seen(k);
+                for (size_t i = 0; i < n && !ambiguous; i++) ambiguous = Sn[i] && V[i] == amb;
+            }
+            if (ambiguous) {
+                if (ctx->path == 2) return tagg_fail(TAGG_ERR_UNSUPPORTED, "f64 min / max over both signed zeros runs on the exact (generic) path; path is forced to stream");
+                es.edge_exact = true;
+                redo = true;
             }
         }
-        if (overflow == 2) return rc = tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
-        if (overflow == 4) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
-        if (overflow == 5) return rc = tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");
-        if (attempt >= 7) return rc = tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
-        // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
-        if (overflow == 1) es.hash_shift += 2;
-        pct_rank_release(es);
-        compact_release(es);
-        cudaFreeAsync(es.arena, es.st); es.arena = nullptr;
-        if (es.d_plan) cudaFreeAsync(es.d_plan, es.st);
-        es.d_plan = nullptr;
-        for (int k = 0; k < 4; k++) {
-            if (es.pct_codes[k]) cudaFreeAsync(es.pct_codes[k], es.st);
-            if (es.pct_buckets[k]) cudaFreeAsync(es.pct_buckets[k], es.st);
-            if (es.pct_count[k]) cudaFreeAsync(es.pct_count[k], es.st);
-            es.pct_codes[k] = nullptr; es.pct_buckets[k] = nullptr; es.pct_count[k] = nullptr;
+        if (!redo) return 0;
+    }
+    drop_result();
+    if (overflow == 3) {  // the rank bins could not resolve this distribution
+        bool cached = false;
+        for (int k = 0; k < 4; k++) cached = cached || (es.rank[k].active && es.rank[k].from_cache);
+        if (cached) {  // ... with thresholds remembered from another docset: sample this one afresh
+            std::lock_guard<std::mutex> g(plan->mu);
+            for (auto& pc : plan->pct_cache) pc.valid = false;
+        } else {
+            es.no_rank = true;  // exact path
         }
     }
+    if (overflow == 2) return tagg_fail(TAGG_ERR_CUDA, "percentile buffer overflow (internal sizing error)");
+    if (overflow == 4) return tagg_fail(TAGG_ERR_BAD_ARG, "a column holds values outside the range its header declares (min_value / num_bits)");
+    if (overflow == 5) return tagg_fail(TAGG_ERR_BAD_ARG, "a sorted-id docset holds ids that are not strictly ascending or >= max_doc of its segment");
+    if (attempt >= 7) return tagg_fail(TAGG_ERR_OOM, "bucket table kept overflowing");
+    // a hash scope ran out of room: grow 4x and redo the pass from clean accumulators
+    if (overflow == 1) es.hash_shift += 2;
+    pct_rank_release(es);
+    compact_release(es);
+    es.cache_release(es.arena); es.arena = nullptr;
+    es.cache_release(es.d_plan);
+    es.d_plan = nullptr;
+    for (int k = 0; k < 4; k++) {
+        if (es.pct_codes[k]) cudaFreeAsync(es.pct_codes[k], es.st);
+        if (es.pct_buckets[k]) cudaFreeAsync(es.pct_buckets[k], es.st);
+        if (es.pct_count[k]) cudaFreeAsync(es.pct_count[k], es.st);
+        es.pct_codes[k] = nullptr; es.pct_buckets[k] = nullptr; es.pct_count[k] = nullptr;
+    }
+    attempt++;
+    *redo_out = true;
+    return 0;
+}
 
+int ExecCall::finish(tagg_result** out) {
+    int rc = 0;
+    for (;;) {
+        bool redo = false;
+        rc = complete(&redo);
+        if (rc) return rc;
+        if (!redo) break;
+        rc = issue();
+        if (rc) return rc;
+    }
     if (collective && !arena_merge) {
         rc = comm_merge_results(es, res);
         if (rc) return rc;
@@ -926,4 +1008,30 @@ int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n
     *out = res;
     ok = true;
     return 0;
+}
+
+int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int mode, int root, tagg_result** out) {
+    if (!plan || !out || (n_inputs && !inputs)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_execute: null argument");
+    ExecCall call;
+    int rc = call.begin(plan, inputs, n_inputs, mode, root);
+    if (rc) return rc;
+    return call.finish(out);
+}
+
+// ---- two queries in flight: begin now, wait later -----------------------------------------------------------------
+struct tagg_pending { ExecCall call; };
+
+int exec_begin(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_pending** out) {
+    if (!plan || !out || (n_inputs && !inputs)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_execute_begin: null argument");
+    auto* p = new tagg_pending();
+    int rc = p->call.begin(plan, inputs, n_inputs, 0, -1);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+int exec_wait(tagg_pending* p, tagg_result** out) {
+    if (!p || !out) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_pending_wait: null argument");
+    int rc = p->call.finish(out);
+    delete p;
+    return rc;
 }

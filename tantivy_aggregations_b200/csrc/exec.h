@@ -133,12 +133,20 @@ struct ExecState {
 
     ~ExecState();
     void free_temps();
+    // scratch from the call slot's block cache (host.h CallRes::blocks); released (kept for the next call) by free_temps or
+    // cache_release.  nullptr: out of memory.
+    void* cache_alloc(size_t bytes);
+    void cache_release(void* p);
+    std::vector<void*> cached;
     // copy a small control block into pinned memory so its upload is asynchronous; falls back to `src`
     const void* pin(const void* src, size_t bytes);
 };
 
 int exec_run(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, int mode, int root,
              tagg_result** out);
+struct tagg_pending;
+int exec_begin(const tagg_plan* plan, const tagg_segment_input* inputs, uint32_t n_inputs, tagg_pending** out);
+int exec_wait(tagg_pending* p, tagg_result** out);
 // compact.cu: device accumulators -> compact image (kernels), its download, the result's directory
 int compact_launch(ExecState& es);
 int compact_download_begin(ExecState& es, tagg_result* res);

@@ -28,9 +28,15 @@ int tagg_fail(int status, const char* fmt, ...);
 // Per-call host resources, pooled in the context: a stream, two events and a pinned staging block
 // (small control uploads and small result downloads go through pinned memory so they are truly async).
 struct CallRes {
+    // Device scratch of the calls that run on this slot (arena, descriptors, ...), kept between calls: a block is only
+    // ever touched on THIS slot's stream.  (Returning it to the stream-ordered pool instead makes the next call in flight —
+    // on another stream — pick the block up with a dependency on this call's tail: two queries in flight then serialise.)
+    struct DevBlock { void* p; size_t bytes; bool in_use; };
+    std::vector<DevBlock> blocks;
     cudaStream_t st = nullptr;   // uploads, downloads, ordering
     cudaStream_t st2 = nullptr;  // upload stream: host docsets cross PCIe here while kernels of earlier chunks run on st
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t chain_ev = nullptr;  // this call's pass AND compaction are done (the next call in flight starts its pass behind it)
     cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, join_ev = nullptr;
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0, pinned_used = 0;
@@ -44,6 +50,12 @@ struct tagg_ctx {
     std::mutex mu;
     std::vector<cudaStream_t> stream_pool;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    // With several calls in flight (tagg_execute_begin) the passes still run one after the other — a persistent pass owns
+    // every SM (its registers leave no room for another block) — so each call's pass explicitly waits for the previous
+    // call's pass AND compaction: its CUDA-event bracket then measures the pass itself and not the queueing behind another
+    // query, and the previous call's small compaction kernels are not starved until this pass ends (their download then
+    // overlaps this pass).  Guarded by mu.
+    cudaEvent_t last_pass_done = nullptr;
     // NCCL (comm.cu), loaded lazily with dlopen so that single-GPU use has no NCCL dependency
     void* nccl = nullptr;  // opaque NcclState*
     int rank = 0, n_ranks = 1;

@@ -673,8 +673,8 @@ int mterms_try(ExecState& es) {
             tb[nseg] = (uint32_t)tiles;
             if (tiles) {
                 uint32_t* d_tb = nullptr;
-                if (cudaMallocAsync((void**)&d_tb, (nseg + 1) * 4, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "tile table allocation failed");
-                es.temps.push_back(d_tb);
+                d_tb = (uint32_t*)es.cache_alloc((nseg + 1) * 4);
+                if (!d_tb) return -tagg_fail(TAGG_ERR_OOM, "tile table allocation failed");
                 if (cudaMemcpyAsync(d_tb, es.pin(tb.data(), (nseg + 1) * 4), (nseg + 1) * 4, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
                     return -tagg_fail(TAGG_ERR_CUDA, "tile table upload failed");
                 MParams sp = p;

@@ -412,8 +412,8 @@ static int stream_launch(ExecState& es, bool first_launch) {
     for (uint32_t mem : covered) es.skip[mem] = 1;
     if (sp.n_tiles == 0) return 1;
     SegDesc* d_descs = nullptr;
-    if (cudaMallocAsync((void**)&d_descs, nseg * sizeof(SegDesc), es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "segment table allocation failed");
-    es.temps.push_back(d_descs);
+    d_descs = (SegDesc*)es.cache_alloc(nseg * sizeof(SegDesc));
+    if (!d_descs) return -tagg_fail(TAGG_ERR_OOM, "segment table allocation failed");
     if (cudaMemcpyAsync(d_descs, es.pin(descs.data(), nseg * sizeof(SegDesc)), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, es.st) != cudaSuccess)
         return -tagg_fail(TAGG_ERR_CUDA, "segment table upload failed");
     sp.segs = d_descs;
@@ -483,8 +483,8 @@ static int stream_launch(ExecState& es, bool first_launch) {
             const uint64_t hdom_min = own ? sp.dom_min : sp.side_dom_min, hdom = own ? sp.dom_size : sp.side_dom;
             if (hist_boundaries(sp.f0, sp.f1, hdom_min, hdom, B)) {
                 uint64_t* d_b = nullptr;
-                if (cudaMallocAsync((void**)&d_b, B.size() * 8, es.st) != cudaSuccess) return -tagg_fail(TAGG_ERR_OOM, "histogram boundary table allocation failed");
-                es.temps.push_back(d_b);
+                d_b = (uint64_t*)es.cache_alloc(B.size() * 8);
+                if (!d_b) return -tagg_fail(TAGG_ERR_OOM, "histogram boundary table allocation failed");
                 if (cudaMemcpyAsync(d_b, es.pin(B.data(), B.size() * 8), B.size() * 8, cudaMemcpyHostToDevice, es.st) != cudaSuccess)
                     return -tagg_fail(TAGG_ERR_CUDA, "histogram boundary table upload failed");
                 sp.hist_bounds = d_b;
