@@ -32,6 +32,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 STATUS, CATEGORY, PRICE, KEYS, VALS, KEYS_SPREAD, KEYS_ZIPF = 0, 1, 2, 3, 4, 5, 6
 TAG_STATUS, TAG_CATEGORY, TAG_PRICE, TAG_KEYS, TAG_VALS = 11, 22, 33, 44, 55

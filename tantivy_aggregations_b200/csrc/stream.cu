@@ -561,6 +561,10 @@ static int stream_launch(ExecState& es, bool first_launch) {
         if (table_bytes + group_bytes(2) > SMEM_MAX) return 0;
         const size_t per3 = SMEM_MAX / (table_bytes + group_bytes(3) + 1024), per2 = SMEM_MAX / (table_bytes + group_bytes(2) + 1024);
         n_stages = (per3 >= 1 && per3 >= std::min<size_t>(per2, 4)) ? 3 : 2;
+        if (const char* ov = getenv("TAGG_STREAM_S")) {  // experiment: ring depth of the one-group-per-CTA shapes
+            const uint32_t st = (uint32_t)atoi(ov);
+            if (st >= 2 && st <= ST_MAXSTAGES && table_bytes + group_bytes(st) <= SMEM_MAX) n_stages = st;
+        }
     }
     sp.n_stages = n_stages;
     sp.group_bytes = (uint32_t)group_bytes(n_stages);

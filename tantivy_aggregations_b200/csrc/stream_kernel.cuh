@@ -12,7 +12,7 @@
 #define ST_TILE TAGG_TILE_DOCS
 #define ST_WORDS_PER_WARP (ST_TILE / 32 / ST_WARPS)  // 8
 #define ST_DOCS_PER_WARP (ST_WORDS_PER_WARP * 32)    // 256
-#define ST_MAXSTAGES 4
+#define ST_MAXSTAGES 6
 #define ST_MAXCOLS 6
 #define ST_MAXPRED 4
 #define ST_MAXBITS (2 + ST_MAXPRED)
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 
             // ---- phase 1: one match-mask word per lane (lanes 0..7) --------------------------------
             uint32_t m = 0;
-            if (lane < ST_WORDS_PER_WARP) {
+            if ((COMPACT || n_valid != ST_TILE || p.n_vpreds) && lane < ST_WORDS_PER_WARP) {
                 const uint32_t wi = warp * ST_WORDS_PER_WARP + lane;
                 const uint32_t d0 = wi * 32;
                 const uint32_t wa = bits_saddr + wi * 4;
