@@ -172,6 +172,14 @@ int tagg_multicolumn_upload(tagg_segment* seg, uint32_t field_id, int kind,
 int tagg_multicolumn_upload_codes(tagg_segment* seg, uint32_t field_id, int kind,
                                   const uint64_t* offsets, size_t n_offsets, /* max_doc+1 */
                                   const uint64_t* codes, size_t n_codes);
+/* A whole tantivy `.fast` CompositeFile (the mmap'd segment file): the footer is parsed on the host and every
+ * requested field's payload(s) go through tagg_column_upload / tagg_multicolumn_upload unchanged — no host decode.
+ * Layout restated from tantivy@14735ce common/composite_file.rs (see csrc/columns.cu); NOT pinned to real tantivy bytes. */
+typedef struct tagg_fast_field { uint32_t field_id; int32_t kind; int32_t multi; } tagg_fast_field;
+int tagg_segment_load_fast_file(tagg_segment* seg, const uint8_t* bytes, size_t len, const tagg_fast_field* fields, uint32_t n_fields);
+/* The directory of such a file (host only, no device needed): (field, idx) and byte range of every payload. */
+int tagg_fast_file_entries(const uint8_t* bytes, size_t len, uint32_t* fields, uint32_t* idxs, uint64_t* begins, uint64_t* ends,
+                           uint32_t cap, uint32_t* n_out);
 /* DeleteBitSet bytes: doc d is DELETED iff bytes[d>>3]>>(d&7)&1 (searcher.rs:41-46). */
 int tagg_segment_set_deletes(tagg_segment* seg, const uint8_t* bytes, size_t len);
 /* Introspection (tests): header and packed bytes of a resident column.

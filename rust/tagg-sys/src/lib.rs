@@ -92,6 +92,14 @@ pub struct tagg_docset {
     pub hi: u64,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct tagg_fast_field {
+    pub field_id: u32,
+    pub kind: i32,
+    pub multi: i32,
+}
+
 /// 64 bytes, `struct tagg_segment_input`: one unit of `collect_segment` work (searcher.rs:27-51).
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -127,6 +135,9 @@ extern "C" {
     pub fn tagg_multicolumn_upload_codes(seg: *mut tagg_segment, field_id: u32, kind: c_int, offsets: *const u64, n_offsets: usize,
                                          codes: *const u64, n_codes: usize) -> c_int;
     pub fn tagg_segment_set_deletes(seg: *mut tagg_segment, bytes: *const u8, len: usize) -> c_int;
+    pub fn tagg_segment_load_fast_file(seg: *mut tagg_segment, bytes: *const u8, len: usize, fields: *const tagg_fast_field, n_fields: u32) -> c_int;
+    pub fn tagg_fast_file_entries(bytes: *const u8, len: usize, fields: *mut u32, idxs: *mut u32, begins: *mut u64, ends: *mut u64,
+                                  cap: u32, n_out: *mut u32) -> c_int;
     pub fn tagg_column_info(seg: *const tagg_segment, field_id: u32, which: c_int, min_value: *mut u64, amplitude: *mut u64,
                             num_bits: *mut u32, n_values: *mut u64, packed_len: *mut u64) -> c_int;
     pub fn tagg_column_download(seg: *const tagg_segment, field_id: u32, which: c_int, out: *mut u8, cap: usize) -> c_int;

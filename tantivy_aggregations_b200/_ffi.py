@@ -37,6 +37,10 @@ class Docset(C.Structure):
                 ("lo", C.c_uint64), ("hi", C.c_uint64)]
 
 
+class FastField(C.Structure):
+    _fields_ = [("field_id", C.c_uint32), ("kind", C.c_int32), ("multi", C.c_int32)]
+
+
 class SegmentInput(C.Structure):
     _fields_ = [("segment", C.c_void_p), ("docset", Docset), ("filters", C.POINTER(Docset)),
                 ("n_filters", C.c_uint32)]
@@ -82,6 +86,8 @@ SYMBOLS = {
     "tagg_multicolumn_upload": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "tagg_multicolumn_upload_codes": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "tagg_segment_set_deletes": (C.c_int, [_P, _P, C.c_size_t]),
+    "tagg_segment_load_fast_file": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_uint32]),
+    "tagg_fast_file_entries": (C.c_int, [_P, C.c_size_t, _P, _P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tagg_column_info": (C.c_int, [_P, C.c_uint32, C.c_int, _U64P, _U64P, C.POINTER(C.c_uint32), _U64P, _U64P]),
     "tagg_column_download": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t]),
     "tagg_plan_create": (C.c_int, [_P, C.POINTER(Node), C.c_uint32, C.POINTER(Blob), C.c_uint32, _PP]),

@@ -539,4 +539,85 @@ def one_of_agg(which, left, right):
     return EitherAgg(which, left if which == "left" else right, False)
 
 
+# ---- beyond the reference: two entries of its TODO list (README.md:31-45) that are pure compositions -----------------
+class Stats:
+    """Fruit of stats_agg_*: count / sum / min / max of a field (avg derived) — README.md:35 "stat"."""
+
+    def __init__(self, count, sum_, min_, max_):
+        self.count, self.sum, self.min, self.max = count, sum_, min_, max_
+
+    @property
+    def avg(self):
+        return None if not self.count or self.sum is None else self.sum / self.count
+
+    def canon(self):
+        return ("stats", self.count, self.sum, self.min, self.max)
+
+    def __repr__(self):
+        return f"Stats(count={self.count}, sum={self.sum}, min={self.min}, max={self.max})"
+
+
+class StatsAgg(Agg):
+    """stats_agg_{u64,i64,f64}[s](field): lowers to (count, sum, min, max) on one column — the fused root / bucket shape of
+    the streaming kernel reads the column once for all four.  `count` counts VALUES for a multi-valued field (documents
+    that reach the leaf for a single-valued one)."""
+
+    def __init__(self, field, kind, multi):
+        self.field, self.kind, self.multi = int(field), kind, int(multi)
+        self.inner = TupleAgg((CountAgg(), SumAgg(field, kind, multi), MinAgg(field, kind, multi), MaxAgg(field, kind, multi)))
+
+    def lower(self, ctx):
+        return self.inner.lower(ctx)
+
+    def decode(self, reader, bucket):
+        c, s, mn, mx = self.inner.decode(reader, bucket)
+        return Stats(c, s, mn, mx)
+
+    def create_fruit(self):
+        return Stats(0, None, None, None)
+
+    def merge(self, acc, fruit):
+        c, s, mn, mx = self.inner.merge((acc.count, acc.sum, acc.min, acc.max), (fruit.count, fruit.sum, fruit.min, fruit.max))
+        return Stats(c, s, mn, mx)
+
+
+def stats_agg_u64(field):
+    return StatsAgg(field, F.U64, 0)
+
+
+def stats_agg_i64(field):
+    return StatsAgg(field, F.I64, 0)
+
+
+def stats_agg_f64(field):
+    return StatsAgg(field, F.F64, 0)
+
+
+def filters_agg(named_queries, sub_factory):
+    """filters_agg({name: query, ...}, lambda: sub) — README.md:40 "filters": one filter_agg per named query over the same
+    sub-aggregation, evaluated in ONE pass (a tuple of FILTER nodes; at most 8 per plan).  Fruit: {name: sub fruit}."""
+    names = list(named_queries)
+    if not 2 <= len(names) <= 8:
+        raise TypeError("filters_agg takes 2..=8 named queries")
+    return _FiltersAgg(names, [FilterAgg(named_queries[n], sub_factory()) for n in names])
+
+
+class _FiltersAgg(Agg):
+    def __init__(self, names, members):
+        self.names, self.inner = names, TupleAgg(tuple(members))
+
+    def lower(self, ctx):
+        return self.inner.lower(ctx)
+
+    def decode(self, reader, bucket):
+        return dict(zip(self.names, self.inner.decode(reader, bucket)))
+
+    def create_fruit(self):
+        return dict(zip(self.names, self.inner.create_fruit()))
+
+    def merge(self, acc, fruit):
+        merged = self.inner.merge(tuple(acc[n] for n in self.names), tuple(fruit[n] for n in self.names))
+        return dict(zip(self.names, merged))
+
+
 FOLD_CTORS = sorted(k for k in _g if k.startswith(("sum_agg_", "min_agg_", "max_agg_")))

@@ -7,6 +7,8 @@
 // re-packed on the device into the same layout (k_pack).
 #include <cub/device/device_scan.cuh>
 
+#include <vector>
+
 #include "host.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -261,6 +263,91 @@ int tagg_column_upload(tagg_segment* seg, uint32_t field_id, int kind, const uin
     if (rc) return rc;
     drop_field(seg, field_id);
     seg->cols[field_id] = c;
+    return 0;
+}
+
+// ---- tantivy CompositeFile (`.fast` file of a segment) -------------------------------------------------------------------
+// Layout restated from tantivy@14735ce src/common/composite_file.rs (external to the reference, see oracle/oracle.cpp
+// header — NOT pinned to real tantivy bytes here: no tantivy in the image):
+//   [payload of (field, idx) #0][payload #1]...[footer][footer_len: u32 LE]
+//   footer = VInt(n) then n x { VInt(offset delta), field: u32 LE, VInt(idx) }, entries ascending by offset;
+//   payload i spans [offset_i, offset_{i+1}) and the last one ends where the footer starts.
+//   VInt (src/common/vint.rs): 7 bits per byte, least significant group first, the LAST byte carries the 0x80 stop bit.
+// A single-valued fast field is (field, 0); a multi-valued one is (field, 0) = offsets column, (field, 1) = values column.
+struct FastEntry { uint32_t field, idx; uint64_t begin, end; };
+static bool read_vint(const uint8_t*& p, const uint8_t* end, uint64_t* out) {
+    uint64_t v = 0;
+    for (int shift = 0; p < end && shift < 64; shift += 7) {
+        const uint8_t b = *p++;
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (b & 0x80) { *out = v; return true; }
+    }
+    return false;
+}
+static int parse_fast_file(const uint8_t* bytes, size_t len, std::vector<FastEntry>& out) {
+    if (!bytes || len < 5) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file shorter than its footer");
+    uint32_t footer_len;
+    memcpy(&footer_len, bytes + len - 4, 4);
+    if ((size_t)footer_len + 4 > len) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file: footer length %u exceeds the file", footer_len);
+    const size_t footer_start = len - 4 - footer_len;
+    const uint8_t *p = bytes + footer_start, *end = bytes + len - 4;
+    uint64_t n = 0, offset = 0;
+    if (!read_vint(p, end, &n) || n > (1u << 20)) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file: malformed footer");
+    out.clear();
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t delta = 0, idx = 0;
+        uint32_t field;
+        if (!read_vint(p, end, &delta) || p + 4 > end) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file: malformed footer entry %llu", (unsigned long long)i);
+        memcpy(&field, p, 4);
+        p += 4;
+        if (!read_vint(p, end, &idx)) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file: malformed footer entry %llu", (unsigned long long)i);
+        offset += delta;
+        if (offset > footer_start) return tagg_fail(TAGG_ERR_BAD_ARG, "fast file: payload offset beyond the footer");
+        if (!out.empty()) out.back().end = offset;
+        out.push_back({field, (uint32_t)idx, offset, footer_start});
+    }
+    return 0;
+}
+
+int tagg_fast_file_entries(const uint8_t* bytes, size_t len, uint32_t* fields, uint32_t* idxs, uint64_t* begins, uint64_t* ends,
+                           uint32_t cap, uint32_t* n_out) {
+    if (!n_out) return tagg_fail(TAGG_ERR_BAD_ARG, "null argument");
+    std::vector<FastEntry> e;
+    int rc = parse_fast_file(bytes, len, e);
+    if (rc) return rc;
+    *n_out = (uint32_t)e.size();
+    for (uint32_t i = 0; i < e.size() && i < cap; i++) {
+        if (fields) fields[i] = e[i].field;
+        if (idxs) idxs[i] = e[i].idx;
+        if (begins) begins[i] = e[i].begin;
+        if (ends) ends[i] = e[i].end;
+    }
+    return 0;
+}
+
+int tagg_segment_load_fast_file(tagg_segment* seg, const uint8_t* bytes, size_t len, const tagg_fast_field* fields, uint32_t n_fields) {
+    if (!seg || (n_fields && !fields)) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_segment_load_fast_file: bad argument");
+    std::vector<FastEntry> e;
+    int rc = parse_fast_file(bytes, len, e);
+    if (rc) return rc;
+    auto find = [&](uint32_t field, uint32_t idx) -> const FastEntry* {
+        for (auto& x : e)
+            if (x.field == field && x.idx == idx) return &x;
+        return nullptr;
+    };
+    for (uint32_t i = 0; i < n_fields; i++) {
+        const tagg_fast_field& f = fields[i];
+        const FastEntry* a = find(f.field_id, 0);
+        if (!a) return tagg_fail(TAGG_ERR_NO_SUCH_COLUMN, "field %u is not in the fast file", f.field_id);
+        if (f.multi) {
+            const FastEntry* b = find(f.field_id, 1);
+            if (!b) return tagg_fail(TAGG_ERR_NO_SUCH_COLUMN, "field %u has no values column in the fast file (not multi-valued?)", f.field_id);
+            rc = tagg_multicolumn_upload(seg, f.field_id, f.kind, bytes + a->begin, (size_t)(a->end - a->begin), bytes + b->begin, (size_t)(b->end - b->begin));
+        } else {
+            rc = tagg_column_upload(seg, f.field_id, f.kind, bytes + a->begin, (size_t)(a->end - a->begin));
+        }
+        if (rc) return rc;
+    }
     return 0;
 }
 

@@ -139,6 +139,16 @@ class Segment:
         if host is not None and self.keep_host:
             self.host[int(field)] = host
 
+    def load_fast_file(self, raw, fields, host=None):
+        """All fast fields of the segment from its tantivy `.fast` CompositeFile bytes.  fields: [(field, kind, multi)]."""
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        arr = (F.FastField * max(1, len(fields)))(*[F.FastField(int(f), int(k), int(m)) for f, k, m in fields])
+        F.check(F.lib().tagg_segment_load_fast_file(self._h, _ptr(buf), len(buf), arr, len(fields)))
+        for f, k, m in fields:
+            self.kinds[int(f)] = (k, int(m))
+        if host and self.keep_host:
+            self.host.update(host)
+
     def synth_column(self, field, kind, recipe, seed, tag, doc_base, a=0, b=1, c=1):
         """Generate a synthetic column on the device (bench / scale tests; SURVEY §8d recipe)."""
         F.check(F.lib().tagg_synth_column(self._h, int(field), int(kind), int(recipe), int(seed), int(tag),

@@ -117,6 +117,32 @@ def product_corpus(empty=False):
     return Corpus([seg])
 
 
+def vint(v):
+    """tantivy VInt (common/vint.rs): 7 bits per byte, least significant group first, the LAST byte carries the stop bit."""
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v == 0:
+            out.append(b | 0x80)
+            return bytes(out)
+        out.append(b)
+
+
+def composite_file(payloads):
+    """A tantivy CompositeFile (common/composite_file.rs, restated): payloads = [((field, idx), bytes)] in write order."""
+    body, entries = bytearray(), []
+    for (field, idx), raw in payloads:
+        entries.append((len(body), field, idx))
+        body += raw
+    footer = bytearray(vint(len(entries)))
+    prev = 0
+    for off, field, idx in entries:
+        footer += vint(off - prev) + struct.pack("<I", field) + vint(idx)
+        prev = off
+    return bytes(body) + bytes(footer) + struct.pack("<I", len(footer))
+
+
 def f64_bits(x):
     return struct.unpack("<Q", struct.pack("<d", float(x)))[0]
 
