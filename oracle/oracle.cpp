@@ -25,7 +25,9 @@
 //     biased quantiles, eps = 0.01).
 //
 // Parity pinning: API-level results are pinned by the reference's own 19 unit tests on the
-// 5-document fixture (tests/golden/reference_tests.json, checked in tests/test_oracle_golden.py).
+// 5-document fixture (corpus: tests/golden/product_fixture.json; the tests themselves: tests/reference_cases.py, run on
+// the oracle by tests/test_oracle_golden.py); f64 min / max / sum around NaN, the signed zeros and the infinities are
+// pinned against a second, independent restatement of minmax.rs:97-106 / sum.rs:95-102 (tests/test_oracle_edge.py).
 // PARITY UNPINNED at: the byte-level column layout (no reference test touches bytes — pinned
 // only against the spec-derived vectors of SURVEY.md Appendix A) and CKMS beyond n = 5
 // (compression never triggers in the reference test; the oracle CKMS is a tolerance witness).

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
     __syncthreads();
     uint32_t cur_seg = 0xffffffffu, seg = 0;
     // the front pays only for skewed keys: every sub-block measures its hit rate over its first two tiles and stops
-    // probing below 1/16 (uniform keys over a large domain: ~10 % of the kernel for nothing); cached entries stay valid
+    // probing below 1/64 (uniform keys over a large domain: ~10 % of the kernel for nothing); cached entries stay valid
     bool use_cache = CACHE;
     uint32_t n_probe = 0, n_hit = 0, tiles_done = 0;
     uint32_t* cstat = (uint32_t*)(ctouch + (1u << MT_CACHE_LOG)) + 2 * sub;  // [probes, hits] of this sub-block
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             n_probe = n_hit = 0;
             if (tiles_done == 2) {
                 named_bar(1 + sub, MT_SUB_THREADS);
-                use_cache = cstat[1] * 16u >= cstat[0];
+                use_cache = cstat[1] * 64u >= cstat[0];
             }
         }
     }

@@ -453,7 +453,12 @@ static int stream_launch(ExecState& es, bool first_launch) {
             if (tf + 3 * group_bytes(2) <= SMEM_MAX || bucket_mode == BK_RANK) { sp.tab_filt = 1; tb = tf; }
             else tb = lay_tables(false);
         }
-        if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX) { stab = true; table_bytes = tb; }
+        // (the CTA-private count tables are u32: the persistent grid spreads the call's tiles evenly over >= 148 CTAs, so a
+        //  CTA counts at most ~1/148 of the call's documents — guard with a factor of two to spare)
+        uint64_t call_docs = 0;
+        for (auto& hs : es.hsegs) call_docs += hs.max_doc;
+        const bool counts_fit_u32 = call_docs < (1ull << 32) * 64;
+        if (tb > 0 && sp.dom_size <= (1u << 20) && tb + group_bytes(2) <= SMEM_MAX && counts_fit_u32) { stab = true; table_bytes = tb; }
         else sp.tab_filt = 0;
         if (sp.tab_filt) {
             for (int g = 0; g < n_bgroups; g++) {

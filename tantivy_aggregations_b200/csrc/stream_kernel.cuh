@@ -389,6 +389,25 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 #pragma unroll
         for (int g = 0; g < (NRG ? NRG : 1); g++) c_rc[g] = c_kc;
         const uint32_t full_saddr = smem_u32(full), empty_saddr = smem_u32(empty);
+        auto flush_tail = [&]() {  // warp-uniform: wtail buffered codes -> the global list
+            __syncwarp();
+            unsigned long long base = 0;
+            uint32_t nlow = 0;
+            for (uint32_t i = lane; i < wtail; i += 32) nlow += lds64(tbuf_saddr + 8 * i) < p.rank_lo ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+            if (lane == 0) {
+                base = atomicAdd(p.tail_count, (unsigned long long)wtail);
+                if (nlow) atomicAdd(p.tail_count + 1, (unsigned long long)nlow);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < wtail; i += 32) {
+                if (base + i < p.tail_cap) p.tail_codes[base + i] = lds64(tbuf_saddr + 8 * i);
+                else *p.overflow_flag = 3u;
+            }
+            __syncwarp();
+            wtail = 0;
+        };
         uint32_t stage = 0, parity = 0;
         for (uint64_t tile = first; tile < p.n_tiles; tile += step) {
             mbar_wait_s(full_saddr + 8 * stage, parity);
@@ -522,25 +541,6 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             if (hb) { hb_first = lds64(hb_saddr); hb_end = lds64(hb_saddr + 8 * hb_dom); }
             const double hb_dmin = (double)(BUCKET == BK_HIST ? p.dom_min : p.side_dom_min);
 
-            auto flush_tail = [&]() {  // warp-uniform: wtail buffered codes -> the global list
-                __syncwarp();
-                unsigned long long base = 0;
-                uint32_t nlow = 0;
-                for (uint32_t i = lane; i < wtail; i += 32) nlow += lds64(tbuf_saddr + 8 * i) < p.rank_lo ? 1u : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
-                if (lane == 0) {
-                    base = atomicAdd(p.tail_count, (unsigned long long)wtail);
-                    if (nlow) atomicAdd(p.tail_count + 1, (unsigned long long)nlow);
-                }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                for (uint32_t i = lane; i < wtail; i += 32) {
-                    if (base + i < p.tail_cap) p.tail_codes[base + i] = lds64(tbuf_saddr + 8 * i);
-                    else *p.overflow_flag = 3u;
-                }
-                __syncwarp();
-                wtail = 0;
-            };
             // U matched documents per lane at a time (independent chains overlap the table latency).
             // CHECK: slots may be empty (act[u] false) — the ragged tail; otherwise every slot is live.
             auto process = [&](auto U_, auto CHECK_, auto POS_, const uint32_t* dl, const bool* act_in) {
@@ -889,24 +889,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
 
         if (CTROOT) fold_root();
         if (BUCKET == BK_TERMS && bad_key && p.overflow_flag) *p.overflow_flag = 4u;
-        if (BUCKET == BK_RANK && wtail) {
-            // (the lambda lives inside the tile loop; same steps here for the last partial buffer)
-            __syncwarp();
-            unsigned long long base = 0;
-            uint32_t nlow = 0;
-            for (uint32_t i = lane; i < wtail; i += 32) nlow += lds64(tbuf_saddr + 8 * i) < p.rank_lo ? 1u : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
-            if (lane == 0) {
-                base = atomicAdd(p.tail_count, (unsigned long long)wtail);
-                if (nlow) atomicAdd(p.tail_count + 1, (unsigned long long)nlow);
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t i = lane; i < wtail; i += 32) {
-                if (base + i < p.tail_cap) p.tail_codes[base + i] = lds64(tbuf_saddr + 8 * i);
-                else *p.overflow_flag = 3u;
-            }
-        }
+        if (BUCKET == BK_RANK && wtail) flush_tail();  // the last partial buffer
         // fold the root accumulators (warp shuffle, then one atomic per warp)
         if (lane == 0 && matched) {
             if (p.n_root_counts > 0) atomicAdd((unsigned long long*)p.root_count_acc[0], (unsigned long long)matched);
