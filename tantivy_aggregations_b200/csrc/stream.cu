@@ -347,9 +347,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
         off += (ST_TILE / 8) * maxnb + 16;
     }
     off = (off + 127) & ~127u;
-    sp.soff_bits = off;
-    off += 256 * ST_MAXBITS;
-    sp.stage_bytes = (off + 127) & ~127u;
+    sp.soff_bits = off;  // (the bitset slots are sized below, once the segments' flags are known)
 
     // per-segment descriptors
     std::vector<SegDesc> descs(nseg);
@@ -394,6 +392,14 @@ static int stream_launch(ExecState& es, bool first_launch) {
                 else if (fd.kind != DS_ALL) d.flags |= SF_PRED_NONE0 << pi;
             }
         }
+    }
+    {   // bitset slots of a stage: slot b sits at 256 * b; only as many as the highest slot any segment uses (shared
+        // memory decides how many consumer groups fit — C5 stages no bitset and gains its third group from this)
+        uint32_t used = 0;
+        for (auto& d : descs) used |= d.flags & 0xffu;
+        const uint32_t n_slots = used ? 32u - (uint32_t)__builtin_clz(used) : 0u;
+        sp.stage_bytes = (sp.soff_bits + 256 * n_slots + 127) & ~127u;
+        if (sp.stage_bytes == 0) sp.stage_bytes = 128;
     }
     for (auto& d : descs) {
         d.tile_bytes = (ST_TILE / 8) * __builtin_popcount(d.flags & 0xffu);
