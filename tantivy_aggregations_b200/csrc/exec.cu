@@ -790,6 +790,7 @@ int ExecCall::issue() {
             if (prev && prev != es.call->chain_ev) CUDA_TRY(cudaStreamWaitEvent(es.st, prev, 0));
         }
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
+        es.launches_at_ev0 = es.n_launches;
         es.skip.assign(es.meta->nodes.size(), 0);
         const bool fast_ok = ctx->path != 1 && !es.edge_exact;
         if (es.edge_exact && ctx->path == 2)

@@ -115,6 +115,7 @@ struct ExecState {
     uint64_t alg_bytes = 0;
     uint64_t direct_bytes = 0;  // host docset bytes the kernels read in place over PCIe
     uint32_t n_launches = 0;
+    uint32_t launches_at_ev0 = 0;  // ev0 is re-recorded right before the first kernel of the pass (stream.cu)
     uint32_t path_used = 0;
     // chunked execute: host docsets are uploaded on a second stream, segments grouped into chunks; the kernels of
     // chunk c wait only for chunk c's uploads (chunk_ev[c]) while later chunks are still crossing PCIe

@@ -545,6 +545,10 @@ static int stream_launch(ExecState& es, bool first_launch) {
         bool ok = false;
         for (auto& c : cand)
             if (table_bytes + c[0] * group_bytes(c[1]) <= SMEM_MAX) { n_groups = c[0]; n_stages = c[1]; ok = true; break; }
+        if (const char* ov = getenv("TAGG_STREAM_GS")) {  // experiment: "groups,stages"
+            uint32_t g = 0, st = 0;
+            if (sscanf(ov, "%u,%u", &g, &st) == 2 && g >= 1 && g <= ST_MAXGROUPS && st >= 2 && st <= ST_MAXSTAGES && table_bytes + g * group_bytes(st) <= SMEM_MAX) { n_groups = g; n_stages = st; }
+        }
         if (!ok) {  // no room for the level bytes: back to the bitmap alone
             nib = false;
             sp.soff_nib = 0;
@@ -618,6 +622,9 @@ static int stream_launch(ExecState& es, bool first_launch) {
         cp.tile_base = t0;
         if (cp.n_tiles == 0) continue;
         if (piped && cudaStreamWaitEvent(kst, es.call->chunk_ev[c], 0) != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "stream ordering failed");
+        // the pass timer (tagg_result_stats kernel_ms) starts at the first kernel of the pass, behind the descriptor
+        // uploads — not at the host-side preparation above
+        if (es.n_launches == es.launches_at_ev0 && es.ev0) cudaEventRecord(es.ev0, kst);
         uint64_t work_units = ((uint64_t)cp.n_tiles + n_groups - 1) / n_groups;
         uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, work_units);
         fn<<<grid, threads, smem_bytes, kst>>>(cp);
