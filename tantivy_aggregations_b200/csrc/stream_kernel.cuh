@@ -439,6 +439,47 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
                     const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
                     const uint8_t* lut = p.pred_lut[i];
+                    if (pc.nb >= 1 && pc.nb <= 2) {
+                        // One- and two-bit columns (status-like fields of <= 4 values): the predicate is a truth table over the
+                        // column's values, evaluated once per tile (lane v tests value v), and applied to 32 documents per lane
+                        // at once on the bit planes of the packed stream — no per-document work at all.  Lane j < 8 produces
+                        // the mask word of documents [32j, 32j + 32) directly in the word-per-lane layout.
+                        const uint64_t minv = ((uint64_t)pc.minhi << 32) | pc.minlo;
+                        bool tv = false;
+                        if (lane < (1u << pc.nb)) {
+                            const uint64_t code = minv + lane;
+                            if (type == PR_LUT) {
+                                const uint64_t r = code - lo;
+                                tv = code >= lo && r < hi && ((lut[r >> 3] >> (r & 7)) & 1);
+                            } else {
+                                tv = code >= lo && code <= hi;
+                            }
+                        }
+                        const uint32_t T = __ballot_sync(0xffffffffu, tv);
+                        uint32_t pm = 0;
+                        if (lane < ST_WORDS_PER_WARP) {
+                            if (pc.nb == 1) {
+                                const uint32_t x = lds32(pc.saddr + (warp * ST_WORDS_PER_WARP + lane) * 4);
+                                pm = ((T & 1u) ? ~x : 0u) | ((T & 2u) ? x : 0u);
+                            } else {
+                                const uint64_t x = lds64(pc.saddr + (warp * ST_WORDS_PER_WARP + lane) * 8);
+                                const uint32_t M0 = (T & 1u) ? 0x55555555u : 0u, M1 = (T & 2u) ? 0x55555555u : 0u;
+                                const uint32_t M2 = (T & 4u) ? 0x55555555u : 0u, M3 = (T & 8u) ? 0x55555555u : 0u;
+                                auto half = [&](uint32_t h) {
+                                    const uint32_t b0 = h, b1 = h >> 1;  // (the table masks keep the even bit positions only)
+                                    uint32_t r = (M0 & ~b1 & ~b0) | (M1 & ~b1 & b0) | (M2 & b1 & ~b0) | (M3 & b1 & b0);
+                                    r = (r | (r >> 1)) & 0x33333333u;
+                                    r = (r | (r >> 2)) & 0x0f0f0f0fu;
+                                    r = (r | (r >> 4)) & 0x00ff00ffu;
+                                    r = (r | (r >> 8)) & 0x0000ffffu;
+                                    return r;
+                                };
+                                pm = half((uint32_t)x) | (half((uint32_t)(x >> 32)) << 16);
+                            }
+                        }
+                        m &= pm;
+                        continue;
+                    }
                     if (pc.nb >= 1 && pc.nb <= 8 && (type == PR_RANGE || hi <= 32)) {
                         // Narrow column (status-like fields): lane l tests documents [8l, 8l + 8) of the warp's 256 from one
                         // 64-bit window of the packed stream, on the packed deltas (the predicate's code range is moved

@@ -304,3 +304,43 @@ def test_histogram_boundary_table_is_bit_exact(ctx, start, interval):
     finally:
         ctx.set_path(F.PATH_AUTO)
     assert dict(hist2._buckets) == dict(hist._buckets)
+
+
+@pytest.mark.parametrize("qname", ["all", "bitset"])
+def test_bit_plane_predicates_on_one_and_two_bit_columns(ctx, qname):
+    """post_filter / column-range predicates on columns of <= 4 values run on the bit planes of the packed stream (32
+    documents per lane, a truth table per tile): every table over the column's values — equality, ranges that clip the
+    domain, empty and full sets, arbitrary closures — on 1- and 2-bit columns with a non-zero min_value, segments whose
+    widths differ (0, 1 and 2 bits), ragged last tiles and deletes; streaming kernel == oracle."""
+    rng = np.random.default_rng(23)
+    BIT, QUAD = 20, 21
+    segs = []
+    for n, quad_vals, bit_vals in ((9001, (5, 6, 7, 8), (3, 4)), (4096, (5, 6), (4, 4)), (2049, (7, 7), (3, 4)), (50_000, (5, 8), (3, 4))):
+        s = SegSpec(n)
+        s.col(QUAD, F.U64, rng.choice(np.array(quad_vals, dtype=np.uint64), size=n))
+        s.col(BIT, F.U64, rng.choice(np.array(bit_vals, dtype=np.uint64), size=n))
+        s.col(PRICE, F.F64, 1.0 + 100.0 * rng.random(n))
+        s.col(CAT, F.U64, rng.integers(1, 40, size=n, dtype=np.uint64))
+        s.deleted = rng.choice(n, size=n // 7, replace=False)
+        segs.append(s)
+    corpus = Corpus(segs)
+    searcher, ox = corpus.build_gpu(ctx), corpus.build_oracle()
+    q = queries(corpus, 9)[qname]
+    sub = lambda: (ta.count_agg(), ta.terms_agg_u64(CAT, (ta.count_agg(), ta.min_agg_f64(PRICE))))
+    preds = [ta.eq(v) for v in (3, 4, 5, 6, 7, 8, 9)] + [ta.ge(6), ta.le(6), ta.lt(5), ta.gt(8), ta.ge(0), ta.in_set({5, 8}), ta.in_set({4}),
+                                                           (lambda c: c % 2 == 1), (lambda c: c != 7), (lambda c: False), (lambda c: True)]
+    ctx.set_path(F.PATH_STREAM)
+    try:
+        for field in (QUAD, BIT):
+            for pr in preds:
+                agg = lambda: ta.post_filter_agg_u64(field, pr, sub())
+                got, reader = searcher.agg_search_with_executor(q, agg(), ta.SINGLE_THREAD, return_reader=True)
+                assert reader.stats()["path"] == 2
+                assert_fruit_equal(got, ox.search(q, agg())[0], F64_SUM_RTOL)
+        # nested: both columns narrow the stream; and a device column-range docset as the main query
+        agg = lambda: ta.post_filter_agg_u64(QUAD, ta.ge(6), ta.post_filter_agg_u64(BIT, ta.eq(4), sub()))
+        assert_fruit_equal(searcher.agg_search(q, agg()), ox.search(q, agg())[0], F64_SUM_RTOL)
+        rq = ta.RangeQuery(QUAD, F.U64, 6, 7, device=True)
+        assert_fruit_equal(searcher.agg_search(rq, sub()), ox.search(rq, sub())[0], F64_SUM_RTOL)
+    finally:
+        ctx.set_path(F.PATH_AUTO)
