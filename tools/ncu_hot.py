@@ -56,3 +56,12 @@ for ln, (s, i, st) in sorted(per.items(), key=lambda kv: -kv[1][0])[:N]:
         if f in src and ln[1] <= len(src[f]): text = src[f][ln[1] - 1].strip()[:90]
     top = ", ".join(f"{k}:{v}" for k, v in st.most_common(2))
     print(f"{100*s/max(ts,1):5.1f}%s {100*i/max(ti,1):5.1f}%i {str(ln[0])+':'+str(ln[1]) if ln else '?':>16} {text:90s} [{top}]")
+if os.environ.get("HOT_BY_LINE"):
+    print("\n# every source line with >= 0.1 % of the executed warp instructions, in source order (instr %, samples %)")
+    for ln, (s, i, st) in sorted(((k, v) for k, v in per.items() if k), key=lambda kv: kv[0]):
+        if 100 * i / max(ti, 1) < 0.1: continue
+        text = ""
+        f = os.path.join(root, "tantivy_aggregations_b200", "csrc", ln[0])
+        if f not in src and os.path.exists(f): src[f] = open(f).read().splitlines()
+        if f in src and ln[1] <= len(src[f]): text = src[f][ln[1] - 1].strip()[:110]
+        print(f"{100*i/max(ti,1):5.2f}%i {100*s/max(ts,1):5.2f}%s {ln[0]}:{ln[1]:<5d} {text}")
