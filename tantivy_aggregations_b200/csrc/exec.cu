@@ -791,6 +791,7 @@ int ExecCall::issue() {
         }
         CUDA_TRY(cudaEventRecord(es.ev0, es.st));
         es.launches_at_ev0 = es.n_launches;
+        es.reserve_sms = agree_pending ? 2u : 0u;
         es.skip.assign(es.meta->nodes.size(), 0);
         const bool fast_ok = ctx->path != 1 && !es.edge_exact;
         if (es.edge_exact && ctx->path == 2)

@@ -115,6 +115,10 @@ struct ExecState {
     uint64_t alg_bytes = 0;
     uint64_t direct_bytes = 0;  // host docset bytes the kernels read in place over PCIe
     uint32_t n_launches = 0;
+    // SMs the persistent kernels leave free: a collective call's key-domain agreement (a one-CTA NCCL all-reduce) is in
+    // flight while the pass runs; a pass that owns every SM leaves one of its own CTAs waiting behind that all-reduce, and
+    // with tiles dealt statically the whole pass then ends that much later (2 GPUs: 1.82 ms instead of 1.54)
+    uint32_t reserve_sms = 0;
     uint32_t launches_at_ev0 = 0;  // ev0 is re-recorded right before the first kernel of the pass (stream.cu)
     uint32_t path_used = 0;
     // chunked execute: host docsets are uploaded on a second stream, segments grouped into chunks; the kernels of

@@ -683,7 +683,8 @@ int mterms_try(ExecState& es) {
                 sp.n_segs = (uint32_t)nseg;
                 sp.n_tiles = (uint32_t)tiles;
                 const uint64_t units = (tiles + n_sub - 1) / n_sub;
-                const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, units);
+                const uint64_t sms = (uint64_t)es.ctx->sm_count > es.reserve_sms ? (uint64_t)es.ctx->sm_count - es.reserve_sms : 1;
+                const uint32_t grid = (uint32_t)std::min<uint64_t>(sms * per_sm, units);
                 fn<<<grid, threads, smem_bytes, es.st>>>(sp);
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_mterms launch failed: %s", cudaGetErrorString(e));

@@ -626,7 +626,8 @@ static int stream_launch(ExecState& es, bool first_launch) {
         // uploads — not at the host-side preparation above
         if (es.n_launches == es.launches_at_ev0 && es.ev0) cudaEventRecord(es.ev0, kst);
         uint64_t work_units = ((uint64_t)cp.n_tiles + n_groups - 1) / n_groups;
-        uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)es.ctx->sm_count * per_sm, work_units);
+        const uint64_t sms = (uint64_t)es.ctx->sm_count > es.reserve_sms ? (uint64_t)es.ctx->sm_count - es.reserve_sms : 1;
+        uint32_t grid = (uint32_t)std::min<uint64_t>(sms * per_sm, work_units);
         fn<<<grid, threads, smem_bytes, kst>>>(cp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -tagg_fail(TAGG_ERR_CUDA, "k_stream launch failed: %s", cudaGetErrorString(e));
