@@ -8,6 +8,7 @@ import pytest
 import tantivy_aggregations_b200 as ta
 from helpers import Corpus, SegSpec
 from tantivy_aggregations_b200 import _ffi as F
+from tantivy_aggregations_b200 import codec
 
 pytestmark = pytest.mark.gpu
 CAT, PRICE, QTY, WIDE = 1, 2, 3, 4
@@ -70,3 +71,30 @@ def test_lazy_result_still_answers_the_plain_readers(world, ctx):
     want, _, _ = ox.search(ta.AllQuery(), ta.terms_agg_u64(CAT, subs()()))
     from helpers import assert_fruit_equal
     assert_fruit_equal(got, want)
+
+
+def test_top_k_edge_sizes_and_a_nested_scope(world):
+    """k = 0, a query that matches nothing, and the inner scope of terms-in-terms selected per parent bucket."""
+    corpus, searcher, ox = world
+    agg = ta.terms_agg_u64(CAT, subs()())
+    assert searcher.terms_top_k(ta.AllQuery(), agg, agg, agg.sub.members[0], 0) == []
+    none = ta.DocIdsQuery({i: np.zeros(0, np.uint32) for i in range(len(corpus.segs))})
+    agg = ta.terms_agg_u64(CAT, subs()())
+    assert searcher.terms_top_k(none, agg, agg, agg.sub.members[0], 10) == []
+    # nested: outer = sign class of QTY via a histogram-free trick (terms on a small i64 field), inner = terms(CAT, count)
+    mk = lambda: ta.terms_agg_i64(QTY, ta.terms_agg_u64(CAT, (ta.count_agg(), ta.max_agg_f64(PRICE))))
+    q = ta.RangeQuery(QTY, F.I64, -3, 3, device=False)
+    want, _, _ = ox.search(q, mk())
+    agg = mk()
+    got, reader = searcher.agg_search_with_executor(q, agg, ta.SINGLE_THREAD, return_reader=True)
+    inner = agg.sub
+    outer_keys, _ = reader.scope(agg.node)
+    assert len(outer_keys) == 7
+    for p, kb in enumerate(outer_keys.tolist()):
+        okey = codec.bits_to_value(F.I64, kb)
+        for by, k in ((0, 5), (1, 40), (0, 10**6)):
+            idx = reader.top_k(inner.node, inner.sub.members[by].node, k, parent_bucket=p)
+            keys, parents = reader.scope_rows(inner.node, idx)
+            assert (parents == p).all()
+            w = want.get(okey).top_k(k, lambda b: b[by])
+            assert keys.tolist() == [key for key, _ in w]
