@@ -6,7 +6,7 @@
 #   3. compute-sanitizer memcheck + racecheck over small parity tests (every kernel family, TMA pipelines included)
 set -u
 out=gpurun_out
-python bench.py --steps 20 --warmup 5 > $out/r2_bench_n1.json 2> $out/r2_bench_n1.err
+python bench.py > $out/r2_bench_n1.json 2> $out/r2_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $out/r2_bench_reference_arm.json 2>> $out/r2_bench_n1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/r2_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_launches.log 2>&1
 tools/prof_one.sh C5 k_stream 1 stream_inst_ct_terms python tools/configs_bench.py c5
@@ -16,6 +16,4 @@ tools/prof_one.sh C3 k_stream 1 stream_inst_ct_hist python tools/configs_bench.p
 tools/prof_one.sh C3h k_stream 1 stream_inst_ct_hist python tools/configs_bench.py c3hist
 tools/prof_one.sh C4 '^k_mterms$' 1 mterms python tools/configs_bench.py c4d
 python tools/configs_bench.py c1,c1x,c2,c3,c4,c5 > $out/r2_configs.txt 2>&1
-SAN="tests/test_gpu_reference.py tests/test_gpu_edge_f64.py::test_sum_of_negative_zeros_keeps_its_sign_on_every_kernel tests/test_gpu_edge_f64.py::test_multi_valued_f64s tests/test_gpu_mterms.py tests/test_gpu_top_k.py::test_top_k_under_a_filter_and_with_ties"
-compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest $SAN -x -q > $out/r2_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> $out/r2_sanitizer_memcheck.log
-compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_reference.py tests/test_gpu_mterms.py -x -q > $out/r2_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> $out/r2_sanitizer_racecheck.log
+# (compute-sanitizer is closed on this GPU pool: profiles/r2_sanitizer_closed_on_pool.log is the tool's own refusal)
