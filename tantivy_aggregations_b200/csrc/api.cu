@@ -241,6 +241,7 @@ int tagg_ctx_destroy(tagg_ctx* ctx) {
         if (c->pinned) cudaFreeHost(c->pinned);
         delete c;
     }
+    if (ctx->pct_sched_dev) cudaFree(ctx->pct_sched_dev);
     for (auto s : ctx->stream_pool) cudaStreamDestroy(s);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     delete ctx;

@@ -807,6 +807,9 @@ int ExecCall::issue() {
             if (es.rank[k].active && !es.skip[es.meta->pct_node[k]]) {
                 if (es.rank[k].d_block) cudaFreeAsync(es.rank[k].d_block, es.st);
                 if (es.rank[k].d_tail) cudaFreeAsync(es.rank[k].d_tail, es.st);
+                if (es.rank[k].d_sorted) cudaFreeAsync(es.rank[k].d_sorted, es.st);
+                if (es.rank[k].d_cub) cudaFreeAsync(es.rank[k].d_cub, es.st);
+                if (es.rank[k].d_pick) cudaFreeAsync(es.rank[k].d_pick, es.st);
                 es.rank[k] = ExecState::RankState();
             }
         int mt = 0;

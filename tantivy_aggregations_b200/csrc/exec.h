@@ -103,6 +103,16 @@ struct ExecState {
         bool from_cache = false;     // thresholds reused from the plan (no sample pass)
         uint32_t node = 0;
         const uint8_t* h_block = nullptr;  // pinned copy of d_block, in flight before the pass's sync (pct_rank_prefetch)
+        // With thresholds (and the list length) remembered from an earlier call, the exact lists are sorted and thinned on
+        // the device right behind the pass, without waiting for their length on the host: the list is pre-filled with
+        // all-ones codes and sorted at the predicted length (the fill sorts to the end), k_tail_pick reads the real
+        // counters on the device.  One synchronisation per query; a list longer than predicted falls back to the host path.
+        uint64_t tail_pred = 0;
+        uint64_t* d_sorted = nullptr;
+        void* d_cub = nullptr;
+        size_t cub_bytes = 0;
+        uint64_t* d_pick = nullptr;
+        const uint64_t* h_pick = nullptr;
     } rank[4];
     bool no_rank = false;            // a rank-bin pass failed its precision check: redo on the exact path
     // f64 MIN / MAX follow the reference's PartialOrd fold (minmax.rs:97-106): per slot, 0 = the order of the codes is

@@ -60,6 +60,9 @@ struct tagg_ctx {
     void* nccl = nullptr;  // opaque NcclState*
     int rank = 0, n_ranks = 1;
 
+    uint64_t* pct_sched_dev = nullptr;  // pct.cu: the geometric rank schedule of the exact lists (uploaded once)
+    uint32_t pct_sched_len = 0;
+
     std::vector<CallRes*> call_pool;
     // freed results are recycled: their arrays keep their capacity, so the next result of the same shape is filled without
     // fresh allocations (a 100 k-bucket result is ~4 MB of vectors: page faults and zero fill were ~40 % of its readout)

@@ -67,8 +67,68 @@ void pct_rank_release(ExecState& es) {
     for (auto& r : es.rank) {
         if (r.d_block) cudaFreeAsync(r.d_block, es.st);
         if (r.d_tail) cudaFreeAsync(r.d_tail, es.st);
+        if (r.d_sorted) cudaFreeAsync(r.d_sorted, es.st);
+        if (r.d_cub) cudaFreeAsync(r.d_cub, es.st);
+        if (r.d_pick) cudaFreeAsync(r.d_pick, es.st);
         r = ExecState::RankState();
     }
+}
+
+// ---- the exact lists, summarised on the device ---------------------------------------------------------------------
+// Ranks kept from an exactly sorted run of n values: every rank up to PICK_DENSE, then geometric with ratio 1 + eps/4.
+// Past PICK_DENSE the sequence does not depend on n (only its end is clamped to n), so it is tabulated once.
+#define PICK_DENSE 4096u
+#define PICK_HIGH 8192u  // the high list is thinned to every (n_high / 4096)-th value: fewer than 8192 of them
+static const std::vector<uint64_t>& geometric_schedule() {
+    static const std::vector<uint64_t> G = [] {
+        std::vector<uint64_t> g;
+        uint64_t r = PICK_DENSE;
+        while (r < (1ull << 40)) {
+            r += std::max<uint64_t>(1, (uint64_t)((double)r * 0.0025));
+            g.push_back(r);
+        }
+        return g;
+    }();
+    return G;
+}
+static inline size_t pick_words(uint32_t sched_len) { return (size_t)PICK_DENSE + sched_len + PICK_HIGH + 1; }
+
+// pick layout: [PICK_DENSE lowest][sched_len geometric ranks of the low list][PICK_HIGH thinned high list][the largest]
+__global__ void k_tail_pick(const uint64_t* __restrict__ sorted, const unsigned long long* __restrict__ tail_count, const uint64_t* __restrict__ sched,
+                            uint32_t sched_len, uint64_t n_sorted, uint64_t* __restrict__ pick) {
+    const uint64_t n_tail = tail_count[0], n_low = tail_count[1];
+    if (n_tail > n_sorted || n_low > n_tail) return;  // longer than predicted: the host path sorts again
+    const uint64_t n_high = n_tail - n_low;
+    const uint64_t step = n_high / 4096 > 1 ? n_high / 4096 : 1;
+    const uint32_t total = PICK_DENSE + sched_len + PICK_HIGH + 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint64_t v = 0;
+        if (i < PICK_DENSE) {
+            if (i < n_low) v = sorted[i];
+        } else if (i < PICK_DENSE + sched_len) {
+            const uint32_t j = i - PICK_DENSE;
+            const uint64_t prev = j ? sched[j - 1] : PICK_DENSE;
+            if (prev < n_low) v = sorted[(sched[j] < n_low ? sched[j] : n_low) - 1];
+        } else if (i < PICK_DENSE + sched_len + PICK_HIGH) {
+            const uint64_t at = (uint64_t)(i - PICK_DENSE - sched_len) * step;
+            if (at < n_high) v = sorted[n_low + at];
+        } else if (n_tail) {
+            v = sorted[n_tail - 1];
+        }
+        pick[i] = v;
+    }
+}
+
+static int sched_on_device(tagg_ctx* ctx) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->pct_sched_dev) return 0;
+    const std::vector<uint64_t>& G = geometric_schedule();
+    uint64_t* d = nullptr;
+    if (cudaMalloc((void**)&d, G.size() * 8) != cudaSuccess) { cudaGetLastError(); return 1; }
+    if (cudaMemcpy(d, G.data(), G.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return 1; }
+    ctx->pct_sched_dev = d;
+    ctx->pct_sched_len = (uint32_t)G.size();
+    return 0;
 }
 
 int pct_rank_plan(ExecState& es, uint32_t node, int k) {
@@ -100,6 +160,25 @@ int pct_rank_plan(ExecState& es, uint32_t node, int k) {
                 R.d_max = R.d_min + R.n_bins;
                 R.d_present = (uint8_t*)(R.d_max + R.n_bins);
                 R.active = true;
+                // the list length of the earlier call predicts this one's: sort and thin the lists behind the pass
+                const uint64_t pred = std::min<uint64_t>(R.tail_cap, pc.tail_seen + pc.tail_seen / 16 + 4096);
+                static const bool no_pick = getenv("TAGG_PCT_HOST_LISTS") != nullptr;  // experiment switch
+                if (!no_pick && pred < (1ull << 31) && sched_on_device(es.ctx) == 0) {
+                    size_t cub_bytes = 0;
+                    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)pred, 0, 64, es.st);
+                    if (cudaMallocAsync((void**)&R.d_sorted, pred * 8 + 16, es.st) == cudaSuccess && cudaMallocAsync(&R.d_cub, cub_bytes + 16, es.st) == cudaSuccess &&
+                        cudaMallocAsync((void**)&R.d_pick, pick_words(es.ctx->pct_sched_len) * 8, es.st) == cudaSuccess &&
+                        cudaMemsetAsync(R.d_tail, 0xff, pred * 8, es.st) == cudaSuccess) {
+                        R.tail_pred = pred;
+                        R.cub_bytes = cub_bytes;
+                    } else {
+                        cudaGetLastError();
+                        if (R.d_sorted) cudaFreeAsync(R.d_sorted, es.st);
+                        if (R.d_cub) cudaFreeAsync(R.d_cub, es.st);
+                        if (R.d_pick) cudaFreeAsync(R.d_pick, es.st);
+                        R.d_sorted = nullptr; R.d_cub = nullptr; R.d_pick = nullptr;
+                    }
+                }
                 return 1;
             }
             cudaGetLastError();
@@ -277,6 +356,18 @@ int pct_rank_prefetch(ExecState& es) {
         if (!h) continue;
         CUDA_TRY(cudaMemcpyAsync(h, R.d_block, bytes, cudaMemcpyDeviceToHost, es.st));
         R.h_block = h;
+        R.h_pick = nullptr;
+        if (R.tail_pred) {
+            const size_t pbytes = pick_words(es.ctx->pct_sched_len) * 8;
+            uint64_t* hp = (uint64_t*)const_cast<void*>(es.pin(nullptr, pbytes));
+            if (!hp) continue;
+            CUDA_TRY(cub::DeviceRadixSort::SortKeys(R.d_cub, R.cub_bytes, (const uint64_t*)R.d_tail, R.d_sorted, (int)R.tail_pred, 0, 64, es.st));
+            k_tail_pick<<<32, 256, 0, es.st>>>(R.d_sorted, R.d_tail_count, es.ctx->pct_sched_dev, es.ctx->pct_sched_len, R.tail_pred, R.d_pick);
+            es.ctx->launches++;
+            es.n_launches++;
+            CUDA_TRY(cudaMemcpyAsync(hp, R.d_pick, pbytes, cudaMemcpyDeviceToHost, es.st));
+            R.h_pick = hp;
+        }
     }
     return 0;
 }
@@ -322,7 +413,34 @@ int pct_rank_collect(ExecState& es, int k) {
 
     // the exact lists: sort, keep every low rank up to 4096 then a geometric schedule; the high end evenly thinned
     std::vector<uint64_t> pos, pos_rank;
-    if (n_tail) {
+    if (n_tail && R.h_pick && n_tail <= R.tail_pred) {
+        // the lists were sorted and thinned on the device (k_tail_pick): the same ranks as below, already on the host
+        const std::vector<uint64_t>& G = geometric_schedule();
+        const uint32_t L = es.ctx->pct_sched_len;
+        const uint64_t* pk = R.h_pick;
+        for (uint64_t r = 1; r <= std::min<uint64_t>(n_low, PICK_DENSE); r++) { S.ranks.push_back(r); S.value_bits.push_back(code_to_f64_bits(pk[r - 1])); }
+        for (uint32_t j = 0; j < L; j++) {
+            const uint64_t prev = j ? G[j - 1] : PICK_DENSE;
+            if (prev >= n_low) break;
+            S.ranks.push_back(std::min<uint64_t>(G[j], n_low));
+            S.value_bits.push_back(code_to_f64_bits(pk[PICK_DENSE + j]));
+        }
+        below = n_low;
+        for (uint32_t b = 0; b < nb; b++) {
+            if (!cnt[b]) continue;
+            S.ranks.push_back(below + 1); S.value_bits.push_back(code_to_f64_bits(~mn[b]));
+            if (cnt[b] > 1) { S.ranks.push_back(below + cnt[b]); S.value_bits.push_back(code_to_f64_bits(mx[b])); }
+            below += cnt[b];
+        }
+        const uint64_t step = std::max<uint64_t>(1, n_high / 4096);
+        uint64_t last_at = 0, i = 0;
+        for (uint64_t at = 0; at < n_high; at += step, i++) {
+            S.ranks.push_back(n_low + n_binned + at + 1);
+            S.value_bits.push_back(code_to_f64_bits(pk[PICK_DENSE + L + i]));
+            last_at = at;
+        }
+        if (n_high && last_at != n_high - 1) { S.ranks.push_back(S.n_total); S.value_bits.push_back(code_to_f64_bits(pk[PICK_DENSE + L + PICK_HIGH])); }
+    } else if (n_tail) {
         uint64_t* d_sorted = nullptr;
         void* d_cub = nullptr;
         size_t cub_bytes = 0;

@@ -88,3 +88,29 @@ def test_rank_bin_percentiles_under_filters(ctx):
     sel = alive & (status <= 2) & (vals > 20.0)
     assert cnt == int(sel.sum())
     check(p, vals[sel])
+
+
+@pytest.mark.parametrize("name", ["uniform_price", "lognormal", "heavy_outliers"])
+def test_repeated_queries_summarise_the_exact_lists_on_the_device(ctx, name):
+    """A prepared plan remembers its thresholds and the length of its exact lists: from the second query on the lists are
+    sorted and thinned on the device behind the pass (pct.cu k_tail_pick) — the summary must be the very same pairs the
+    host path of the first query produced.  A docset that doubles the lists outruns the prediction and falls back."""
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+    vals = distributions(rng)[name]
+    half = N // 2
+    segs = [SegSpec(half).col(PRICE, F.F64, vals[:half]), SegSpec(N - half).col(PRICE, F.F64, vals[half:])]
+    searcher = Corpus(segs).build_gpu(ctx)
+    m = rng.random(N) < 0.4
+    q = ta.BitsetQuery({0: np.packbits(m[:half].astype(np.uint8), bitorder="little"), 1: np.packbits(m[half:].astype(np.uint8), bitorder="little")})
+    plan = searcher.prepare(ta.percentiles_agg_f64(PRICE))
+    first = searcher.agg_search(q, plan)
+    check(first, vals[m])
+    for _ in range(3):
+        again = searcher.agg_search(q, plan)
+        assert again.n == first.n and again.ranks == first.ranks and again.values == first.values
+    everything = searcher.agg_search(ta.AllQuery(), plan)   # 2.5x the documents: longer lists than predicted
+    check(everything, vals)
+    again = searcher.agg_search(ta.AllQuery(), plan)
+    assert again.ranks == everything.ranks and again.values == everything.values
+    back = searcher.agg_search(q, plan)
+    assert back.ranks == first.ranks and back.values == first.values

@@ -16,7 +16,12 @@ def run(name, S, q, mk, reps=4):
         _, r = S.agg_search_with_executor(q, plan, ta.SINGLE_THREAD, return_reader=True)
         st = r.stats()
         best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
-    print(f"{name:52s} path={best['path']} kernel={best['kernel_ms']:9.3f} ms  alg={best['alg_bytes']/1e6:8.0f} MB  {best['alg_bytes']/best['kernel_ms']/1e6:7.0f} GB/s  launches={best['n_launches']}", flush=True)
+    import time
+    t0 = time.perf_counter()
+    for _ in range(8):
+        f = S.agg_search(q, plan)
+    step_ms = (time.perf_counter() - t0) / 8 * 1e3
+    print(f"{name:52s} path={best['path']} kernel={best['kernel_ms']:9.3f} ms  step={step_ms:7.3f} ms  alg={best['alg_bytes']/1e6:8.0f} MB  {best['alg_bytes']/best['kernel_ms']/1e6:7.0f} GB/s  launches={best['n_launches']}", flush=True)
 
 def segs_of(n, nseg, cols):
     out = []
