@@ -31,6 +31,7 @@
 #define MT_TILE 1024     // documents per sub-block tile
 #define MT_TILE_BITS 10
 #define MT_CHUNK 4096    // key occurrences expanded at a time
+#define MT_STAGE (MT_CHUNK * 2 / 8)  // leaf values staged at a time (the expansion buffer, as 64-bit codes)
 #define MT_MAXGROUPS 2
 #define MT_MAXPRED NARROW_MAXPRED
 #define MT_MAXCOUNTS 2
@@ -116,6 +117,35 @@ __device__ __forceinline__ void l2_prefetch_values(const ColS& c, uint64_t lo, u
     if (bytes > (1u << 20)) bytes = 1u << 20;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((uint32_t)bytes) : "memory");
 }
+// Entries first, first + 1, ... of a column relative to `first`: 32-bit arithmetic per entry (i * nb stays small inside a tile).
+// Rel32: packed DELTAS of a narrow column (nb <= 32) — offsets columns, whose min_value cancels in differences.
+struct Rel32 { const uint32_t* wp; uint32_t sh0, nb, mask; };
+__device__ __forceinline__ Rel32 rel32_at(const ColS& c, uint64_t first) {
+    const uint64_t bit0 = first * c.nb;
+    Rel32 r;
+    r.wp = (const uint32_t*)c.words + (bit0 >> 5); r.sh0 = (uint32_t)bit0 & 31u; r.nb = c.nb; r.mask = (uint32_t)c.mask;
+    return r;
+}
+__device__ __forceinline__ uint32_t rel32_delta(const Rel32& r, uint32_t i) {
+    const uint32_t bb = r.sh0 + i * r.nb;
+    const uint32_t* w = r.wp + (bb >> 5);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), bb & 31u) & r.mask;
+}
+// RelCol: codes of a column of any width
+struct RelCol { const uint64_t* wp; uint64_t mask, minv; uint32_t sh0, nb; };
+__device__ __forceinline__ RelCol rel_at(const ColS& c, uint64_t first) {
+    const uint64_t bit0 = first * c.nb;
+    RelCol r;
+    r.wp = c.words + (bit0 >> 6); r.sh0 = (uint32_t)bit0 & 63u; r.nb = c.nb; r.mask = c.mask; r.minv = c.minv;
+    return r;
+}
+__device__ __forceinline__ uint64_t rel_get(const RelCol& r, uint32_t j) {
+    const uint32_t bb = r.sh0 + j * r.nb;
+    const uint64_t* w = r.wp + (bb >> 6);
+    const uint32_t sh = bb & 63u;
+    const uint64_t lo = __ldg(w), hi = __ldg(w + 1);
+    return (((lo >> sh) | ((hi << 1) << (63u - sh))) & r.mask) + r.minv;
+}
 __device__ __forceinline__ void cols_load(ColS* dst, const DevColumn& c) {
     dst->words = c.words; dst->minv = c.min_value; dst->mask = c.mask; dst->nb = c.num_bits; dst->pad = 0;
 }
@@ -176,7 +206,9 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
         }
         const uint32_t d0 = ((uint32_t)tile - __ldg(p.tile_begin + seg)) * MT_TILE;
         const uint32_t nd = min((uint32_t)MT_TILE, S.max_doc - d0);
-        const uint64_t kbase = p.key_multi ? cget(cs[0], d0) : (uint64_t)d0;
+        const bool koff32 = p.key_multi && cs[0].nb <= 32;  // narrow offsets: every column of < 2^32 values
+        const uint32_t kd0 = koff32 ? rel32_delta(rel32_at(cs[0], d0), 0) : 0u;
+        const uint64_t kbase = koff32 ? (uint64_t)kd0 + cs[0].minv : p.key_multi ? cget(cs[0], d0) : (uint64_t)d0;
         const bool plain = S.main.kind == DS_ALL && !S.has_deletes && p.n_preds == 0;
         // ---- L2 prefetch of the sub-block's NEXT tile: fixed-position slices (offset columns) now, the
         //      value slices (whose position depends on the offsets at the tile's ends) after the doc phase
@@ -197,70 +229,135 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             }
         }
         // ---- doc phase: MT_DU documents per thread in flight --------------------------------------------
+        // Offsets (key idx, leaf idx) are unpacked by consecutive threads from consecutive packed entries — coalesced, in
+        // 32-bit arithmetic relative to the tile's first entry (the column's min_value cancels in the differences).  A
+        // multi-valued leaf is then folded from shared memory: the tile's value slice [idx[d0], idx[d0 + nd]) is unpacked
+        // one value per thread (coalesced again) into the chunk buffer, and each document folds its own range there.  The
+        // thread-per-document walk idx -> vals it replaces was a chain of dependent, scattered L2 loads: 40 % of the
+        // kernel's stall samples (profiles/r2_ncu_hot_C4.txt).
         {
-            uint32_t di_[MT_DU], fl[MT_DU];
-            uint64_t ga[MT_DU][NG ? NG : 1], ge[MT_DU][NG ? NG : 1];
+            uint32_t fl[MT_DU];
+            const Rel32 kr = rel32_at(cs[0], d0);
 #pragma unroll
             for (int u = 0; u < MT_DU; u++) {
                 const uint32_t i = st + u * MT_SUB_THREADS;
-                di_[u] = i;
                 fl[u] = 0;
-                if (i < nd) koff[i] = p.key_multi ? (uint32_t)(cget(cs[0], d0 + i) - kbase) : i;
-                if (u == 0 && st == 0) koff[nd] = p.key_multi ? (uint32_t)(cget(cs[0], (uint64_t)d0 + nd) - kbase) : nd;
                 if (i >= nd) continue;
-                const uint32_t doc = d0 + i;
-                const bool ok = plain || doc_matches(S, p.preds, p.n_preds, doc);
-                fl[u] = ok ? 1u : 0u;
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    ga[u][g] = doc; ge[u][g] = ok ? (uint64_t)doc + 1 : doc;
-                    if (p.groups[g].multi) {
-                        ga[u][g] = cget(cs[2 + 2 * g], doc);
-                        ge[u][g] = ok ? cget(cs[2 + 2 * g], (uint64_t)doc + 1) : ga[u][g];
-                    }
-                }
+                koff[i] = !p.key_multi ? i : koff32 ? rel32_delta(kr, i) - kd0 : (uint32_t)(cget(cs[0], d0 + i) - kbase);
+                fl[u] = (plain || doc_matches(S, p.preds, p.n_preds, d0 + i)) ? 1u : 0u;
             }
+            if (st == 0) koff[nd] = !p.key_multi ? nd : koff32 ? rel32_delta(kr, nd) - kd0 : (uint32_t)(cget(cs[0], (uint64_t)d0 + nd) - kbase);
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 const MGroup& G = p.groups[g];
+                const ColS& oc = cs[2 + 2 * g];
                 const ColS& vc = cs[3 + 2 * g];
                 uint64_t sum[MT_DU], mn[MT_DU], mx[MT_DU];  // min in max-form (~code), like the arena
+                bool has[MT_DU];
 #pragma unroll
-                for (int u = 0; u < MT_DU; u++) { sum[u] = G.kind == TAGG_F64 ? NEG_ZERO_BITS : 0ull; mn[u] = 0; mx[u] = 0; }  // f64 sums fold from -0.0
-                for (uint64_t r = 0;; r++) {  // round r: the r-th value of each of the thread's documents
-                    uint64_t code[MT_DU];
-                    bool live[MT_DU], any = false;
-#pragma unroll
-                    for (int u = 0; u < MT_DU; u++) {
-                        live[u] = fl[u] && ga[u][g] + r < ge[u][g];
-                        code[u] = live[u] ? cget(vc, ga[u][g] + r) : 0;
-                        any = any || live[u];
+                for (int u = 0; u < MT_DU; u++) { sum[u] = G.kind == TAGG_F64 ? NEG_ZERO_BITS : 0ull; mn[u] = 0; mx[u] = 0; has[u] = false; }  // f64 sums fold from -0.0
+                auto fold = [&](int u, uint64_t code) {
+                    if (G.ops & MO_SUM) {
+                        if (G.kind == TAGG_F64) sum[u] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)sum[u]), code_to_f64(code)));
+                        else sum[u] += code_to_bits(G.kind, code);
                     }
-                    if (!any) break;
+                    if (G.ops & MO_MIN) mn[u] = max(mn[u], ~code);
+                    if (G.ops & MO_MAX) mx[u] = max(mx[u], code);
+                };
+                if (G.multi && oc.nb <= 32) {
+                    // staged: the ranges live in the group's first contribution array until they are in registers
+                    uint32_t* voff = (uint32_t*)(base + ((G.ops & MO_SUM) ? G.soff_sum : (G.ops & MO_MIN) ? G.soff_min : G.soff_max));
+                    uint64_t* stage = (uint64_t*)docof;  // MT_STAGE codes; the expansion buffer is idle during the doc phase
+                    const Rel32 vr = rel32_at(oc, d0);
+                    const uint32_t vd0 = rel32_delta(vr, 0);
+                    const uint64_t vbase = (uint64_t)vd0 + oc.minv;  // index of the tile's first value
 #pragma unroll
                     for (int u = 0; u < MT_DU; u++) {
-                        if (!live[u]) continue;
-                        if (G.ops & MO_SUM) {
-                            if (G.kind == TAGG_F64) sum[u] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)sum[u]), code_to_f64(code[u])));
-                            else sum[u] += code_to_bits(G.kind, code[u]);
+                        const uint32_t i = st + u * MT_SUB_THREADS;
+                        if (i < nd) voff[i] = rel32_delta(vr, i) - vd0;
+                    }
+                    if (st == 0) voff[nd] = rel32_delta(vr, nd) - vd0;
+                    named_bar(1 + sub, MT_SUB_THREADS);
+                    uint32_t ga[MT_DU], ge[MT_DU];
+#pragma unroll
+                    for (int u = 0; u < MT_DU; u++) {
+                        const uint32_t i = st + u * MT_SUB_THREADS;
+                        ga[u] = ge[u] = 0;
+                        if (i < nd && fl[u]) { ga[u] = voff[i]; ge[u] = voff[i + 1]; }
+                        has[u] = ge[u] > ga[u];
+                    }
+                    const uint32_t nv = voff[nd];
+                    named_bar(1 + sub, MT_SUB_THREADS);  // every range is in registers: voff's array may be written, the buffer filled
+                    for (uint32_t vb = 0; vb < nv; vb += MT_STAGE) {
+                        const uint32_t cn = min((uint32_t)MT_STAGE, nv - vb);
+                        const RelCol rv = rel_at(vc, vbase + vb);
+                        for (uint32_t j = st; j < cn; j += MT_SUB_THREADS) stage[j] = rel_get(rv, j);
+                        named_bar(1 + sub, MT_SUB_THREADS);
+                        uint32_t lo[MT_DU], hi[MT_DU];
+#pragma unroll
+                        for (int u = 0; u < MT_DU; u++) { lo[u] = max(ga[u], vb); hi[u] = min(ge[u], vb + cn); }
+                        for (uint32_t r = 0;; r++) {  // round r: the r-th value (inside this chunk) of each of the thread's documents
+                            uint64_t code[MT_DU];
+                            bool live[MT_DU], any = false;
+#pragma unroll
+                            for (int u = 0; u < MT_DU; u++) {
+                                live[u] = lo[u] + r < hi[u];
+                                code[u] = live[u] ? stage[lo[u] + r - vb] : 0;
+                                any = any || live[u];
+                            }
+                            if (!any) break;
+#pragma unroll
+                            for (int u = 0; u < MT_DU; u++)
+                                if (live[u]) fold(u, code[u]);
                         }
-                        if (G.ops & MO_MIN) mn[u] = max(mn[u], ~code[u]);
-                        if (G.ops & MO_MAX) mx[u] = max(mx[u], code[u]);
+                        named_bar(1 + sub, MT_SUB_THREADS);
+                    }
+                } else {
+                    uint64_t ga[MT_DU], ge[MT_DU];
+#pragma unroll
+                    for (int u = 0; u < MT_DU; u++) {
+                        const uint32_t doc = d0 + st + u * MT_SUB_THREADS;
+                        ga[u] = ge[u] = 0;
+                        if (!fl[u]) continue;
+                        ga[u] = doc; ge[u] = (uint64_t)doc + 1;
+                        if (G.multi) { ga[u] = cget(oc, doc); ge[u] = cget(oc, (uint64_t)doc + 1); }
+                        has[u] = ge[u] > ga[u];
+                    }
+                    for (uint64_t r = 0;; r++) {  // round r: the r-th value of each of the thread's documents
+                        uint64_t code[MT_DU];
+                        bool live[MT_DU], any = false;
+#pragma unroll
+                        for (int u = 0; u < MT_DU; u++) {
+                            live[u] = ga[u] + r < ge[u];
+                            code[u] = live[u] ? cget(vc, ga[u] + r) : 0;
+                            any = any || live[u];
+                        }
+                        if (!any) break;
+#pragma unroll
+                        for (int u = 0; u < MT_DU; u++)
+                            if (live[u]) fold(u, code[u]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < MT_DU; u++) {
-                    if (fl[u] && ge[u][g] > ga[u][g]) {
+                    if (has[u]) {
+                        const uint32_t i = st + u * MT_SUB_THREADS;
                         fl[u] |= 2u << g;
-                        if (G.ops & MO_SUM) ((uint64_t*)(base + G.soff_sum))[di_[u]] = sum[u];
-                        if (G.ops & MO_MIN) ((uint64_t*)(base + G.soff_min))[di_[u]] = mn[u];
-                        if (G.ops & MO_MAX) ((uint64_t*)(base + G.soff_max))[di_[u]] = mx[u];
+                        if (G.ops & MO_SUM) ((uint64_t*)(base + G.soff_sum))[i] = sum[u];
+                        if (G.ops & MO_MIN) ((uint64_t*)(base + G.soff_min))[i] = mn[u];
+                        if (G.ops & MO_MAX) ((uint64_t*)(base + G.soff_max))[i] = mx[u];
+                        // a contribution equal to the accumulator's identity leaves no trace in the cell: the value phase sets
+                        // the Option flag explicitly for these documents (SEEN_DERIVED)
+                        const uint64_t own = G.derive_op == MO_SUM ? sum[u] : G.derive_op == MO_MIN ? mn[u] : mx[u];
+                        if (G.seen_mode == SEEN_DERIVED && own == (G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull)) fl[u] |= 8u << g;
                     }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < MT_DU; u++)
-                if (di_[u] < nd) flags[di_[u]] = (uint8_t)fl[u];
+            for (int u = 0; u < MT_DU; u++) {
+                const uint32_t i = st + u * MT_SUB_THREADS;
+                if (i < nd) flags[i] = (uint8_t)fl[u];
+            }
         }
         if (pf_col >= 0) l2_prefetch_values(cs[pf_col], pf_lo, pf_hi);
         named_bar(1 + sub, MT_SUB_THREADS);
@@ -353,12 +450,11 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                         for (int u = 0; u < MT_U; u++)
                             if (((f[u] >> (1 + g)) & 1u) && !G.seen[b[u]]) G.seen[b[u]] = 1;
                     } else if (G.seen_mode == SEEN_DERIVED) {  // a contribution equal to the identity leaves no trace in the
-                        // cell (min / max: the smallest / largest code; f64 sum: a document whose values are all -0.0)
-                        const uint64_t* ss = (const uint64_t*)(base + (G.derive_op == MO_SUM ? G.soff_sum : G.derive_op == MO_MIN ? G.soff_min : G.soff_max));
-                        const uint64_t ident = G.derive_op == MO_SUM ? NEG_ZERO_BITS : 0ull;
+                        // cell (min / max: the smallest / largest code; f64 sum: a document whose values are all -0.0): the
+                        // doc phase marked those documents (flag bit 3 + g)
 #pragma unroll
                         for (int u = 0; u < MT_U; u++)
-                            if (((f[u] >> (1 + g)) & 1u) && ss[di[u]] == ident) G.seen[b[u]] = 1;
+                            if ((f[u] >> (3 + g)) & 1u) G.seen[b[u]] = 1;
                     }
                 }
 #pragma unroll
@@ -403,6 +499,7 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
             }
             named_bar(1 + sub, MT_SUB_THREADS);
         }
+        if (nk == 0) named_bar(1 + sub, MT_SUB_THREADS);  // (a tile without keys: nobody may still read koff[nd] when the next tile writes it)
         if (CACHE && use_cache && ++tiles_done <= 2) {
             n_probe = __reduce_add_sync(0xffffffffu, n_probe);
             n_hit = __reduce_add_sync(0xffffffffu, n_hit);

@@ -74,15 +74,24 @@ def test_mterms_huge_fanout_and_ragged_docs(ctx):
     lists[2999] = list(rng.integers(0, 500, size=9000))
     s = SegSpec(n)
     s.mcol(TAGS, F.U64, lists)
-    s.mcol(FVALS, F.F64, [list(np.round(rng.random(rng.integers(0, 3)) * 10, 3)) for _ in range(n)])
+    fv = [list(np.round(rng.random(rng.integers(0, 3)) * 10, 3)) for _ in range(n)]
+    # leaf values are folded from a 1024-value staging buffer: documents whose values span several fills of it, a
+    # range that ends exactly on a fill boundary, values of a deleted document in between
+    fv[9] = list(np.round(rng.random(2500) * 10, 3))
+    fv[1600] = list(np.round(rng.random(1100) * 10, 3))
+    fv[2050] = list(np.round(rng.random(1024 - sum(len(x) for x in fv[2048:2050])) * 10, 3))
+    fv[8] = list(np.round(rng.random(700) * 10, 3))
+    s.mcol(FVALS, F.F64, fv)
     s.deleted = [0, 8, 2998]
     corpus = Corpus([s])
     searcher, ox = corpus.build_gpu(ctx), corpus.build_oracle()
-    mk = lambda: ta.terms_agg_u64s(TAGS, (ta.count_agg(), ta.sum_agg_f64s(FVALS), ta.max_agg_f64s(FVALS)))
-    want, _, _ = ox.search(ta.AllQuery(), mk())
-    got, reader = searcher.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, return_reader=True)
-    assert reader.stats()["path"] == PATH_MTERMS
-    assert_fruit_equal(got, want, RTOL)
+    for mk in (lambda: ta.terms_agg_u64s(TAGS, (ta.count_agg(), ta.sum_agg_f64s(FVALS), ta.max_agg_f64s(FVALS))),
+               lambda: ta.terms_agg_u64s(TAGS, ta.sum_agg_f64s(FVALS)),
+               lambda: ta.terms_agg_u64s(TAGS, (ta.min_agg_f64s(FVALS), ta.sum_agg_u64s(TAGS)))):
+        want, _, _ = ox.search(ta.AllQuery(), mk())
+        got, reader = searcher.agg_search_with_executor(ta.AllQuery(), mk(), ta.SINGLE_THREAD, return_reader=True)
+        assert reader.stats()["path"] == PATH_MTERMS
+        assert_fruit_equal(got, want, RTOL)
 
 
 def test_mterms_hashed_growth_multi_valued_keys(ctx):
