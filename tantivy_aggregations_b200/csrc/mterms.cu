@@ -433,11 +433,21 @@ __global__ void __launch_bounds__(MT_SUB_THREADS * MT_MAXSUB, 1) k_mterms(const 
                         }
                     }
                 } else {
+                    // the home slots of all MT_U keys are read at once (independent L2 loads); a key found there is done — at
+                    // load <= 3/4 most are — and only the rest walk the probe sequence one dependent load at a time
+                    const uint64_t hmask = p.scope.capacity - 1;
+                    uint64_t home[MT_U], hkey[MT_U];
+#pragma unroll
+                    for (int u = 0; u < MT_U; u++) {
+                        home[u] = hash_key(key[u], 0) >> __clzll(hmask);
+                        hkey[u] = f[u] ? __ldcg(p.scope.keys + home[u]) : 0ull;
+                    }
 #pragma unroll
                     for (int u = 0; u < MT_U; u++) {
                         b[u] = 0;
                         if (!f[u]) continue;
-                        b[u] = scope_lookup(p.overflow, p.scope, 0, key[u]);
+                        // (an all-zero cell is ambiguous — empty or key 0 — and takes the state-checked path)
+                        b[u] = (hkey[u] != 0 && hkey[u] == key[u]) ? (uint32_t)home[u] : scope_lookup(p.overflow, p.scope, 0, key[u]);
                         if (b[u] == INVALID_BUCKET) { f[u] = 0; b[u] = 0; }
                     }
                 }
