@@ -576,9 +576,11 @@ inline uint64_t f64_as_u64_saturating(double x) {  // Rust `as u64` (saturating,
 }
 struct HistSeg : SegNode {
     const Node* sub_node; const Column* col; double start, interval;
+    uint32_t kind = TAGG_F64;  // i64 / date keys (date_histogram, README.md:41 TODO list): the value as f64, exact below 2^53
     std::unique_ptr<SegNode> sub;
     void collect(uint32_t doc, Fruit& f) override {  // histogram.rs:136-152
-        double k = code_to_f64(col->get(doc));
+        const uint64_t code = col->get(doc);
+        double k = kind == TAGG_F64 ? code_to_f64(code) : kind == TAGG_U64 ? (double)code : (double)(long long)(code ^ 0x8000000000000000ull);
         if (k != k) return;
         double n = k - start;
         if (n < 0.0) return;
@@ -598,7 +600,7 @@ struct HistNode : Node {
         // the reference .unwrap()s here (histogram.rs:81) and panics; the restatement reports it
         if (it == ctx.seg->cols.end()) { err = TAGG_ERR_NO_SUCH_COLUMN; return nullptr; }
         auto s = std::make_unique<HistSeg>();
-        s->sub_node = kids[0].get(); s->col = &it->second; s->start = d.f0; s->interval = d.f1;
+        s->sub_node = kids[0].get(); s->col = &it->second; s->start = d.f0; s->interval = d.f1; s->kind = d.kind;
         s->sub = kids[0]->for_segment(ctx, err);
         if (!s->sub) return nullptr;
         return s;

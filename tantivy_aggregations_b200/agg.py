@@ -205,12 +205,13 @@ class TermsAgg(Agg):
 class HistogramAgg(Agg):
     """histogram_agg_f64(field, start, interval, sub) — src/bucket/histogram.rs:9-21"""
 
-    def __init__(self, field, start, interval, sub):
+    def __init__(self, field, start, interval, sub, kind=F.F64):
         self.field, self.start, self.interval = int(field), float(start), float(interval)
         self.sub = as_agg(sub)
+        self.kind = kind  # f64 in the reference; date / i64 keys: date_histogram_agg below
 
     def lower(self, ctx):
-        self.node = ctx.emit(op=F.OP_HISTOGRAM, kind=F.F64, field_id=self.field, n_children=1,
+        self.node = ctx.emit(op=F.OP_HISTOGRAM, kind=self.kind, field_id=self.field, n_children=1,
                              f0=self.start, f1=self.interval)
         self.sub.lower(ctx)
         return self.node
@@ -618,6 +619,72 @@ class _FiltersAgg(Agg):
     def merge(self, acc, fruit):
         merged = self.inner.merge(tuple(acc[n] for n in self.names), tuple(fruit[n] for n in self.names))
         return dict(zip(self.names, merged))
+
+
+def date_histogram_agg(field, interval_seconds, sub, start=0, kind=F.DATE):
+    """date_histogram_agg(field, interval, sub) — README.md:41 "date_histogram": fixed-width buckets over a date fast field
+    (seconds since the epoch, i64 codec — SURVEY §8 E1), ordinal = floor((t - start) / interval) by the arithmetic of
+    histogram.rs:136-152 on the timestamp as f64 (exact below 2^53); documents before `start` are skipped like the
+    reference's `n < 0`.  Fruit: Histogram whose bucket keys are `start + ord * interval` (timestamps)."""
+    if not interval_seconds > 0:
+        raise ValueError("date_histogram_agg needs a positive interval")
+    return HistogramAgg(field, float(start), float(interval_seconds), sub, kind=kind)
+
+
+class Cardinality:
+    """Fruit of cardinality_agg_*: the EXACT number of distinct values (an HLL sketch, README.md:36, would estimate it);
+    the distinct keys ride along so fruits of different shards merge exactly."""
+
+    def __init__(self, keys=()):
+        self.keys = set(keys)
+
+    @property
+    def value(self):
+        return len(self.keys)
+
+    def canon(self):
+        return ("cardinality", tuple(sorted(self.keys)))
+
+    def __repr__(self):
+        return f"Cardinality({self.value})"
+
+
+class CardinalityAgg(Agg):
+    """cardinality_agg_{u64,i64}[s](field) — README.md:36 "cardinality": lowers to terms_agg(field, count_agg()); the
+    bucket table the pass builds anyway IS the distinct set (dense tables: one existence byte per value of the column's
+    domain; wide domains: the open-addressing spill table), compacted on the device."""
+
+    def __init__(self, field, kind, multi):
+        self.inner = TermsAgg(field, kind, multi, CountAgg())
+
+    def lower(self, ctx):
+        return self.inner.lower(ctx)
+
+    def decode(self, reader, bucket):
+        keys, _ = reader.scope_children(self.inner.node, bucket)
+        return Cardinality(codec.bits_to_value(self.inner.kind, k) for k in keys)
+
+    def create_fruit(self):
+        return Cardinality()
+
+    def merge(self, acc, fruit):
+        return Cardinality(acc.keys | fruit.keys)
+
+
+def cardinality_agg_u64(field):
+    return CardinalityAgg(field, F.U64, 0)
+
+
+def cardinality_agg_i64(field):
+    return CardinalityAgg(field, F.I64, 0)
+
+
+def cardinality_agg_u64s(field):
+    return CardinalityAgg(field, F.U64, 1)
+
+
+def cardinality_agg_i64s(field):
+    return CardinalityAgg(field, F.I64, 1)
 
 
 FOLD_CTORS = sorted(k for k in _g if k.startswith(("sum_agg_", "min_agg_", "max_agg_")))

@@ -102,8 +102,9 @@ static int analyse(PlanMeta& m, uint32_t& pos, int parent, int scope, int depth)
             want_lo = want_hi = 1;
             break;
         case TAGG_OP_HISTOGRAM:
-            if (d.kind != TAGG_F64 || d.multi)
-                return tagg_fail(TAGG_ERR_BAD_PLAN, "node %u: histogram_agg_f64 reads a single-valued f64 field (histogram.rs:9-21)", me);
+            // f64 keys: histogram_agg_f64 (histogram.rs:9-21); i64 / date keys: date_histogram (README.md:41, beyond the reference)
+            if ((d.kind != TAGG_F64 && d.kind != TAGG_I64 && d.kind != TAGG_DATE) || d.multi)
+                return tagg_fail(TAGG_ERR_BAD_PLAN, "node %u: histogram_agg reads a single-valued f64 (or i64 / date) field (histogram.rs:9-21)", me);
             want_lo = want_hi = 1;
             break;
         case TAGG_OP_FILTER:

@@ -61,8 +61,10 @@ __device__ __forceinline__ uint64_t code_to_bits(uint32_t kind, uint64_t c) {
 
 // histogram.rs:136-152 — exact IEEE: n = k - start; ord = floor(n / interval) as u64 (saturating).
 // Returns false when the document is skipped (NaN or n < 0).
-__device__ __forceinline__ bool hist_ord(uint64_t code, double start, double interval, uint64_t* ord) {
-    double k = code_to_f64(code);
+// `kind` is the key column's type: f64 in the reference; i64 / date keys (date_histogram, README.md:41 — seconds since the
+// epoch) are converted to f64 first, exact below 2^53.
+__device__ __forceinline__ bool hist_ord(uint64_t code, double start, double interval, uint64_t* ord, uint32_t kind = TAGG_F64) {
+    double k = kind == TAGG_F64 ? code_to_f64(code) : kind == TAGG_U64 ? (double)code : (double)(long long)(code ^ 0x8000000000000000ull);
     if (k != k) return false;
     double n = __dsub_rn(k, start);
     if (n < 0.0) return false;

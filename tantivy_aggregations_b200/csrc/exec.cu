@@ -398,12 +398,12 @@ static int scope_domains_local(ExecState& es, std::vector<uint64_t>& dom, std::v
                     dense_ok = 0;
                 } else {
                     uint64_t olo = 0, ohi = 0;
-                    bool vlo = hist_ord_h(lo, start, interval, &olo);
-                    bool vhi = hist_ord_h(hi, start, interval, &ohi);
+                    bool vlo = hist_ord_h(lo, start, interval, &olo, nd.kind);
+                    bool vhi = hist_ord_h(hi, start, interval, &ohi, nd.kind);
                     if (!vlo) olo = 0;  // the smallest valid k is >= start, whose ordinal is >= 0
                     if (!vhi) {
                         double khi = code_to_f64_h(hi);
-                        ohi = (khi != khi && (hi >> 63)) ? ~0ull : olo;  // +NaN codes lie above +inf; below start: nothing valid
+                        ohi = (nd.kind == TAGG_F64 && khi != khi && (hi >> 63)) ? ~0ull : olo;  // +NaN codes lie above +inf; below start: nothing valid
                     }
                     if (ohi < olo) ohi = olo;
                     dmin = olo;

@@ -14,8 +14,8 @@ inline double code_to_f64_h(uint64_t c) {
     return d;
 }
 // host twin of dev.cuh hist_ord (IEEE double arithmetic is identical on both sides)
-inline bool hist_ord_h(uint64_t code, double start, double interval, uint64_t* ord) {
-    double k = code_to_f64_h(code);
+inline bool hist_ord_h(uint64_t code, double start, double interval, uint64_t* ord, uint32_t kind = TAGG_F64) {
+    double k = kind == TAGG_F64 ? code_to_f64_h(code) : kind == TAGG_U64 ? (double)code : (double)(long long)(code ^ 0x8000000000000000ull);
     if (k != k) return false;
     volatile double n = k - start;
     if (n < 0.0) return false;

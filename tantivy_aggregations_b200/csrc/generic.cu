@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_generic(const DevPlan* __restrict__ P, 
                 }
                 case TAGG_OP_HISTOGRAM: {  // histogram.rs:136-152
                     uint64_t ord;
-                    if (!hist_ord(col_get(S.cols[nd.col], doc), nd.f0, nd.f1, &ord)) { pc = nd.end; break; }
+                    if (!hist_ord(col_get(S.cols[nd.col], doc), nd.f0, nd.f1, &ord, nd.kind)) { pc = nd.end; break; }
                     uint32_t b = scope_lookup(P->overflow, P->scopes[nd.own_scope], bucket, ord);
                     if (b == INVALID_BUCKET || sp >= TAGG_MAX_DEPTH) { pc = nd.end; break; }
                     Frame& f = frames[sp++];

@@ -277,7 +277,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
             // histogram_agg_f64(same column, interval, count_agg()) in the same tuple: fused (BASELINE config C3)
             for (uint32_t h : members) {
                 const tagg_node& hn = m.nodes[h];
-                if (es.skip[h] || hn.op != TAGG_OP_HISTOGRAM || hn.multi || m.col_slot[h] != m.col_slot[mem]) continue;
+                if (es.skip[h] || hn.op != TAGG_OP_HISTOGRAM || hn.kind != TAGG_F64 || hn.multi || m.col_slot[h] != m.col_slot[mem]) continue;
                 const ScopeLayout& HL = es.scopes[m.own_scope[h]];
                 if (HL.mode != SCOPE_DENSE || HL.dom_size > 256 || HL.capacity != HL.dom_size) continue;
                 if (m.end[h] != h + 2 || m.nodes[h + 1].op != TAGG_OP_COUNT) continue;
@@ -292,6 +292,7 @@ static int stream_launch(ExecState& es, bool first_launch) {
             }
         } else if (nd.op == TAGG_OP_TERMS || nd.op == TAGG_OP_HISTOGRAM) {
             if (bucket_mode != BK_NONE || nd.multi) continue;  // one bucket node per launch; multi-valued: generic kernel
+            if (nd.op == TAGG_OP_HISTOGRAM && nd.kind != TAGG_F64) continue;  // date_histogram (integer keys): generic kernel
             const int sc = m.own_scope[mem];
             const ScopeLayout& L = es.scopes[sc];
             if (L.mode != SCOPE_DENSE) continue;

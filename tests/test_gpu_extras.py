@@ -51,3 +51,81 @@ def test_filters_agg_one_pass(world):
     for name, q in named.items():
         want, _, _ = ox.search(ta.AllQuery(), ta.filter_agg(q, sub()))
         assert_fruit_equal(got[name], want, 1e-12, name)
+
+
+DATE_F, TAGS_F = 4, 5
+
+
+@pytest.fixture(scope="module")
+def dated(ctx):
+    rng = np.random.default_rng(33)
+    segs = []
+    for n in (40_000, 0, 9_001):
+        s = SegSpec(n)
+        s.col(CAT, F.U64, rng.integers(1, 12, size=n, dtype=np.uint64))
+        # two years of second-resolution timestamps around a day boundary, a few before the epoch
+        t = rng.integers(1_500_000_000, 1_563_000_000, size=n, dtype=np.int64)
+        t[: n // 100] = rng.integers(-86_400 * 3, 86_400 * 3, size=n // 100)
+        s.col(DATE_F, F.DATE, t)
+        s.col(PRICE, F.F64, 1.0 + 100.0 * rng.random(n))
+        s.mcol(TAGS_F, F.U64, [list(rng.integers(0, 3000, size=rng.integers(0, 4), dtype=np.uint64)) for _ in range(n)])
+        s.deleted = range(0, n, 13)
+        segs.append(s)
+    corpus = Corpus(segs)
+    return corpus, corpus.build_gpu(ctx), corpus.build_oracle()
+
+
+def _alive(s):
+    m = np.ones(s.max_doc, dtype=bool)
+    m[list(s.deleted)] = False
+    return m
+
+
+def test_date_histogram(dated):
+    """README.md:41 date_histogram: daily / 30-day buckets over a date fast field, against the oracle (same arithmetic,
+    histogram.rs:136-152 on the timestamp) and against numpy's integer floor division."""
+    from tantivy_aggregations_b200 import codec
+    corpus, searcher, ox = dated
+    ts = np.concatenate([codec.code_to_i64(s.cols[DATE_F][1])[_alive(s)] for s in corpus.segs])
+    for interval, start in ((86_400, 0), (30 * 86_400, 1_500_000_000), (3_600, -86_400 * 3)):
+        mk = lambda: ta.date_histogram_agg(DATE_F, interval, (ta.count_agg(), ta.max_agg_f64(PRICE)), start=start)
+        got = searcher.agg_search(ta.AllQuery(), mk())
+        want, _, _ = ox.search(ta.AllQuery(), mk())
+        assert_fruit_equal(got, want, 1e-12, f"date_histogram {interval}")
+        ok = ts >= start
+        ords, counts = np.unique((ts[ok] - start) // interval, return_counts=True)
+        assert {o: v[0] for o, v in got._buckets.items()} == {int(o): int(c) for o, c in zip(ords, counts)}
+        keys = [k for k, _ in got.buckets()]
+        assert keys[0] == start + int(ords[0]) * interval
+    # nested under terms, under a filter
+    mk = lambda: ta.filter_agg(ta.RangeQuery.half_open(PRICE, F.F64, 10.0, 60.0),
+                               ta.terms_agg_u64(CAT, ta.date_histogram_agg(DATE_F, 7 * 86_400, ta.count_agg())))
+    want, _, _ = ox.search(ta.AllQuery(), mk())
+    assert_fruit_equal(searcher.agg_search(ta.AllQuery(), mk()), want, 1e-12, "nested date_histogram")
+
+
+def test_cardinality(dated):
+    """README.md:36 cardinality: the exact distinct count of a field — root, multi-valued, nested per bucket — against
+    numpy, and merged across shards like any fruit."""
+    from tantivy_aggregations_b200 import codec
+    corpus, searcher, ox = dated
+    cats = np.concatenate([s.cols[CAT][1][_alive(s)] for s in corpus.segs])
+    assert searcher.agg_search(ta.AllQuery(), ta.cardinality_agg_u64(CAT)).value == len(np.unique(cats))
+    tags = set()
+    for s in corpus.segs:
+        kind, off, codes = s.mcols[TAGS_F]
+        al = _alive(s)
+        for d in np.nonzero(al)[0]:
+            tags.update(codes[int(off[d]):int(off[d + 1])].tolist())
+    got = searcher.agg_search(ta.AllQuery(), ta.cardinality_agg_u64s(TAGS_F))
+    assert got.value == len(tags) and got.keys == tags
+    # nested: distinct days per category == the explicit terms through the oracle
+    day = lambda: ta.terms_agg_u64(CAT, ta.cardinality_agg_u64s(TAGS_F))
+    got = searcher.agg_search(ta.AllQuery(), day())
+    want, _, _ = ox.search(ta.AllQuery(), ta.terms_agg_u64(CAT, ta.terms_agg_u64s(TAGS_F, ta.count_agg())))
+    assert {k: c.value for k, c in got.res.items()} == {k: len(t.res) for k, t in want.res.items()}
+    # shard merge (PreparedAgg::merge on the host): two halves of the index
+    agg = ta.cardinality_agg_u64s(TAGS_F)
+    a = ta.Searcher(searcher.ctx, searcher.segments[:1]).agg_search(ta.AllQuery(), ta.cardinality_agg_u64s(TAGS_F))
+    b = ta.Searcher(searcher.ctx, searcher.segments[1:]).agg_search(ta.AllQuery(), ta.cardinality_agg_u64s(TAGS_F))
+    assert agg.merge(agg.merge(agg.create_fruit(), a), b).value == len(tags)
