@@ -65,14 +65,19 @@ impl<T> Histogram<T> {
         res
     }
 }
-pub struct HistogramAggF64<A> { field: Field, start: f64, interval: f64, sub: A }
+pub struct HistogramAggF64<A> { field: Field, start: f64, interval: f64, kind: u8, sub: A }
 pub fn histogram_agg_f64<A: Agg>(field: Field, start: f64, interval: f64, sub: A) -> HistogramAggF64<A> {
-    HistogramAggF64 { field, start, interval, sub }
+    HistogramAggF64 { field, start, interval, kind: sys::TAGG_F64, sub }
+}
+/// README.md:41 "date_histogram" (beyond the reference): fixed-width buckets over a date fast field (seconds since the
+/// epoch); the same node with a date key — ordinal = floor((t - start) / interval), documents before `start` skipped.
+pub fn date_histogram_agg<A: Agg>(field: Field, interval_seconds: u64, start: i64, sub: A) -> HistogramAggF64<A> {
+    HistogramAggF64 { field, start: start as f64, interval: interval_seconds as f64, kind: sys::TAGG_DATE, sub }
 }
 impl<A: Agg> Agg for HistogramAggF64<A> {
     type Fruit = Histogram<A::Fruit>;
     fn emit_plan<'q>(&'q self, plan: &mut PlanBuilder<'q>) -> u32 {
-        let me = plan.emit(sys::tagg_node { op: sys::TAGG_OP_HISTOGRAM, kind: sys::TAGG_F64, field_id: self.field.0, n_children: 1,
+        let me = plan.emit(sys::tagg_node { op: sys::TAGG_OP_HISTOGRAM, kind: self.kind, field_id: self.field.0, n_children: 1,
                                             f0: self.start, f1: self.interval, ..Default::default() });
         self.sub.emit_plan(plan);
         me
@@ -88,6 +93,20 @@ impl<A: Agg> Agg for HistogramAggF64<A> {
         Ok(Histogram { start: self.start, interval: self.interval, buckets })
     }
     fn n_nodes(&self) -> u32 { 1 + self.sub.n_nodes() }
+}
+
+/// README.md:36 "cardinality" (beyond the reference): the exact number of distinct values of a u64 fast field — the
+/// bucket table of `terms_agg_u64(field, count_agg())` IS the distinct set; only its length is read back.
+pub struct CardinalityAggU64 { inner: TermsAggU64<crate::metric::CountAgg> }
+pub fn cardinality_agg_u64(field: Field) -> CardinalityAggU64 { CardinalityAggU64 { inner: terms_agg_u64(field, crate::metric::count_agg()) } }
+impl Agg for CardinalityAggU64 {
+    type Fruit = u64;
+    fn emit_plan<'q>(&'q self, plan: &mut PlanBuilder<'q>) -> u32 { self.inner.emit_plan(plan) }
+    fn read_fruit(&self, res: &ResultReader, node: u32, bucket: u32) -> Result<Self::Fruit> {
+        let (_, parents) = res.scope(node)?;
+        Ok(parents.iter().filter(|&&p| p == bucket).count() as u64)
+    }
+    fn n_nodes(&self) -> u32 { self.inner.n_nodes() }
 }
 
 /// filter_agg(&query, sub) (filter.rs:8-16): the second query's matched docs become one more docset per segment.

@@ -897,6 +897,8 @@ int ExecCall::issue() {
         }
         CUDA_TRY(cudaMemcpyAsync(&flags[0], es.arena + es.off_overflow, 4, cudaMemcpyDeviceToHost, es.st));
         if (es.d_bad_ids) CUDA_TRY(cudaMemcpyAsync(&flags[1], es.d_bad_ids, 4, cudaMemcpyDeviceToHost, es.st));
+        flags[2] = flags[3] = 0;
+        if (es.mt_front_node >= 0 && flags != flags_local) CUDA_TRY(cudaMemcpyAsync(&flags[2], es.arena + es.off_overflow + 8, 8, cudaMemcpyDeviceToHost, es.st));
         return 0;
     }
 }
@@ -912,6 +914,10 @@ int ExecCall::complete(bool* redo_out) {
     ms_total += ms;
     uint32_t overflow = flags[0];
     bool redo = overflow != 0;
+    if (es.mt_front_node >= 0 && flags[2]) {  // the hot-key front's measured hit rate (mterms.cu): remembered with the plan
+        std::lock_guard<std::mutex> g(es.plan->mu);
+        es.plan->mt_front_hint[es.mt_front_node] = (uint64_t)flags[3] * 64u >= flags[2] ? 1 : 2;
+    }
     if (!overflow) {
         for (int k = 0; k < 4 && !redo; k++)
             if (es.rank[k].active) {

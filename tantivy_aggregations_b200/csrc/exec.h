@@ -69,6 +69,7 @@ struct ExecState {
     std::vector<uint64_t> n_cand;    // candidates per segment (ids count or max_doc)
     std::vector<void*> temps;        // device allocations to release at the end
     uint32_t* d_bad_ids = nullptr;   // set by k_ids_to_bitset when a SORTED_IDS filter docset is malformed
+    int mt_front_node = -1;          // TERMS node whose k_mterms launch measures its hot-key front (control words 2, 3)
 
     std::vector<ScopeLayout> scopes;
     std::vector<SlotLayout> slots;

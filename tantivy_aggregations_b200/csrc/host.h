@@ -144,6 +144,9 @@ struct tagg_plan {
     tagg_ctx* ctx = nullptr;
     std::shared_ptr<PlanMeta> meta;
     mutable PctThresholds pct_cache[4];  // guarded by mu
+    // k_mterms' shared-memory hot-key front, per TERMS node: 0 = measure, 1 = it found reuse, 2.. = it did not (counts the
+    // queries since, mterms.cu); guarded by mu
+    mutable uint8_t mt_front_hint[64] = {};  // TAGG_MAX_NODES (dev.cuh)
     int readout = 0;                     // TAGG_READOUT_*
     std::vector<uint8_t*> d_blobs;  // device copies of LUT bitmaps
     // multi-GPU: the key domains agreed across ranks on the previous collective call of this plan; reused optimistically
