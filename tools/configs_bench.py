@@ -66,7 +66,7 @@ if "c3" in which:
     run("C3 percentiles(price) 500M/50%", S, q, lambda: ta.percentiles_agg_f64(PRICE), reps=2)
     run("C3 (hist, percentiles) 500M/50%", S, q, lambda: (ta.histogram_agg_f64(PRICE, 0.0, 10.0, ta.count_agg()), ta.percentiles_agg_f64(PRICE)), reps=2)
     for s in segs: s.close()
-if "c4" in which or "c4d" in which or "c4z" in which:
+if "c4" in which or "c4d" in which or "c4z" in which or "c4h" in which:
     segs = segs_of(250_000_000, 16, [lambda s, b: s.synth_multicolumn(KEYS, ta.U64, 1, SEED, 44, b, 9, 0, 1_000_000),
                                      lambda s, b: s.synth_multicolumn(KEYS_SPREAD, ta.U64, 2, SEED, 44, b, 9, 5, 1_000_000, 1 << 20),
                                      lambda s, b: s.synth_multicolumn(6, ta.U64, 3, SEED, 44, b, 9, 0, 1_000_000),
@@ -74,7 +74,7 @@ if "c4" in which or "c4d" in which or "c4z" in which:
     S = ta.Searcher(ctx, segs)
     if "c4" in which or "c4d" in which:
         run("C4 terms_u64s(keys, sum_f64s(vals)) dense 1M keys", S, ta.AllQuery(), lambda: ta.terms_agg_u64s(KEYS, ta.sum_agg_f64s(VALS)), reps=3)
-    if "c4" in which:
+    if "c4" in which or "c4h" in which:
         run("C4 same, hashed spill table (40-bit key domain)", S, ta.AllQuery(), lambda: ta.terms_agg_u64s(KEYS_SPREAD, ta.sum_agg_f64s(VALS)), reps=3)
     if "c4" in which or "c4z" in which:
         run("C4 same, power-law keys (dense table + hot-key front)", S, ta.AllQuery(), lambda: ta.terms_agg_u64s(6, ta.sum_agg_f64s(VALS)), reps=3)
