@@ -336,9 +336,10 @@ template <class Sub>
 struct HistogramAgg {  // histogram_agg_f64(field, start, interval, sub) — src/bucket/histogram.rs:9-21
     using Fruit = Histogram<typename Sub::Fruit>;
     Field field; double start, interval; Sub sub;
+    uint8_t kind = TAGG_F64;  // TAGG_DATE / TAGG_I64: date_histogram_agg below
     mutable uint32_t node = 0;
     void emit(PlanBuilder& pb) const {
-        tagg_node n{}; n.op = TAGG_OP_HISTOGRAM; n.kind = TAGG_F64; n.field_id = field; n.n_children = 1; n.f0 = start; n.f1 = interval; node = pb.emit(n);
+        tagg_node n{}; n.op = TAGG_OP_HISTOGRAM; n.kind = kind; n.field_id = field; n.n_children = 1; n.f0 = start; n.f1 = interval; node = pb.emit(n);
         sub.emit(pb);
     }
     Fruit read(const ResultReader& r, uint32_t bucket) const {
@@ -348,6 +349,25 @@ struct HistogramAgg {  // histogram_agg_f64(field, start, interval, sub) — src
     }
 };
 template <class Sub> HistogramAgg<Sub> histogram_agg_f64(Field f, double start, double interval, Sub s) { return {f, start, interval, s}; }
+// Beyond the reference (its README.md:31-45 TODO list): fixed-width buckets over a date fast field (seconds since the
+// epoch), ordinal = floor((t - start) / interval) by the arithmetic of histogram.rs:136-152 on the timestamp
+template <class Sub> HistogramAgg<Sub> date_histogram_agg(Field f, uint64_t interval_seconds, Sub s, int64_t start = 0) {
+    return {f, (double)start, (double)interval_seconds, s, TAGG_DATE};
+}
+
+// cardinality_agg_{u64,i64}[s](field): the EXACT distinct count — the bucket table of terms_agg(field, count_agg()) is the
+// distinct set (README.md:36 names an estimate; exact is inside any estimator's tolerance)
+template <class K, bool MULTI>
+struct CardinalityAgg {
+    using Fruit = uint64_t;
+    TermsAgg<K, MULTI, CountAgg> inner;
+    void emit(PlanBuilder& pb) const { inner.emit(pb); }
+    Fruit read(const ResultReader& r, uint32_t bucket) const { return children(r, inner.node, bucket).size(); }
+};
+inline CardinalityAgg<uint64_t, false> cardinality_agg_u64(Field f) { return {{f, CountAgg(), nullptr}}; }
+inline CardinalityAgg<int64_t, false> cardinality_agg_i64(Field f) { return {{f, CountAgg(), nullptr}}; }
+inline CardinalityAgg<uint64_t, true> cardinality_agg_u64s(Field f) { return {{f, CountAgg(), nullptr}}; }
+inline CardinalityAgg<int64_t, true> cardinality_agg_i64s(Field f) { return {{f, CountAgg(), nullptr}}; }
 
 template <class Sub>
 struct FilterAgg {  // filter_agg(&query, sub) — src/filter.rs:8-16; borrows the query like FilterAgg<'q>

@@ -109,6 +109,14 @@ int main() {
         // post_filter.rs:330-345
         CHECK(searcher.agg_search_with_executor(all, post_filter_agg_f64(schema.price, gt(5.0), count_agg()), ex) == 4);
     }
+    {   // beyond the reference (its TODO list, README.md:31-45): date_histogram and cardinality on the fixture
+        auto days = searcher.agg_search(all, date_histogram_agg(schema.date_created, 86400, count_agg()));
+        CHECK(days.bucket_map.size() == 3 && days.bucket_map.at(0) == 1 && days.bucket_map.at(18261) == 2 && days.bucket_map.at(18262) == 2);
+        auto cats = searcher.agg_search(all, terms_agg_u64(schema.category_id, count_agg()));
+        CHECK(searcher.agg_search(all, cardinality_agg_u64(schema.category_id)) == cats.res.size());
+        auto tags = searcher.agg_search(all, terms_agg_u64s(schema.tag_ids, count_agg()));
+        CHECK(searcher.agg_search(all, cardinality_agg_u64s(schema.tag_ids)) == tags.res.size());
+    }
     // FastFieldNotAvailableError (sum.rs:50-55); the reference's histogram panics instead (histogram.rs:81)
     bool threw = false;
     try { searcher.agg_search(all, sum_agg_u64(42)); } catch (const FastFieldNotAvailableError&) { threw = true; }
