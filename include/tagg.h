@@ -172,6 +172,10 @@ int tagg_multicolumn_upload(tagg_segment* seg, uint32_t field_id, int kind,
 int tagg_multicolumn_upload_codes(tagg_segment* seg, uint32_t field_id, int kind,
                                   const uint64_t* offsets, size_t n_offsets, /* max_doc+1 */
                                   const uint64_t* codes, size_t n_codes);
+/* The address column of a segment: a u64 fast field whose value for document d is base + d, generated on the device.  Not a
+ * tantivy fast field: it gives documents a key, so that "the matched documents with the k best values of a field"
+ * (top_hits, reference README.md:31-45) is a terms aggregation keyed by it (Searcher.top_hits in the Python mirror). */
+int tagg_segment_doc_address_column(tagg_segment* seg, uint32_t field_id, uint64_t base);
 /* A whole tantivy `.fast` CompositeFile (the mmap'd segment file): the footer is parsed on the host and every
  * requested field's payload(s) go through tagg_column_upload / tagg_multicolumn_upload unchanged — no host decode.
  * Layout restated from tantivy@14735ce common/composite_file.rs (see csrc/columns.cu); NOT pinned to real tantivy bytes. */

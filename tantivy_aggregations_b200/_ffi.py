@@ -83,6 +83,7 @@ SYMBOLS = {
     "tagg_segment_max_doc": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "tagg_column_upload": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t]),
     "tagg_column_upload_codes": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t]),
+    "tagg_segment_doc_address_column": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
     "tagg_multicolumn_upload": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "tagg_multicolumn_upload_codes": (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "tagg_segment_set_deletes": (C.c_int, [_P, _P, C.c_size_t]),

@@ -465,6 +465,32 @@ int tagg_column_download(const tagg_segment* seg, uint32_t field_id, int which, 
     return 0;
 }
 
+// ---- document address column (include/tagg.h) ---------------------------------------------------
+__global__ void k_iota(uint64_t base, uint64_t n, uint64_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = base + i;
+}
+int tagg_segment_doc_address_column(tagg_segment* seg, uint32_t field_id, uint64_t base) {
+    if (!seg) return tagg_fail(TAGG_ERR_BAD_ARG, "tagg_segment_doc_address_column: null segment");
+    tagg_ctx* ctx = seg->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t n = seg->max_doc;
+    uint64_t* d = nullptr;
+    if (n) CUDA_TRY(cudaMalloc(&d, n * 8));
+    cudaStream_t st = ctx->acquire_stream();
+    if (n) {
+        k_iota<<<grid_for(n, ctx->sm_count), 256, 0, st>>>(base, n, d);
+        ctx->launches++;
+    }
+    HostColumn col;
+    int rc = column_from_device_codes(ctx, TAGG_U64, d, n, &col, st);
+    ctx->release_stream(st);
+    if (d) cudaFree(d);
+    if (rc) return rc;
+    drop_field(seg, field_id);
+    seg->cols[field_id] = col;
+    return 0;
+}
+
 // ---- synthetic generators ------------------------------------------------------------------------
 int tagg_synth_column(tagg_segment* seg, uint32_t field_id, int kind, int recipe, uint64_t seed, uint64_t tag,
                       uint64_t doc_base, uint64_t a, uint64_t b, uint64_t c) {

@@ -160,6 +160,13 @@ class Segment:
                                                int(doc_base), int(count_mod), int(a), int(b), int(c)))
         self.kinds[int(field)] = (kind, 1)
 
+    def add_doc_address_column(self, field, base):
+        """A u64 fast field whose value for document d is base + d, generated on the device (tagg_segment_doc_address_column):
+        the key column of Searcher.top_hits_f64."""
+        F.check(F.lib().tagg_segment_doc_address_column(self._h, int(field), int(base)))
+        self.kinds[int(field)] = (F.U64, 0)
+        self._doc_addr = (int(field), int(base))
+
     def set_deletes(self, deleted_docs=None, raw=None):
         """DeleteBitSet: either an iterable of deleted doc ids or the raw bitset bytes."""
         if raw is None:
@@ -602,6 +609,42 @@ class Searcher:
     def agg_search(self, query, agg):
         """src/searcher.rs:13-17 — default executor is SingleThread."""
         return self.agg_search_with_executor(query, agg, SINGLE_THREAD)
+
+    DOC_ADDR_FIELD = 0xFFFFFFF0  # field id of the generated address column (segment ordinal << 32 | doc id)
+
+    def top_hits_f64(self, query, field, k, descending=True):
+        """top_hits (reference README.md:31-45, TODO there): the k matched documents with the largest (smallest) values of an
+        f64 fast field, as [(value, segment ordinal, doc id)] — ties in document order.  Two passes of existing kernels, no
+        per-document host work: (1) percentiles_agg_f64(field) — its fruit is a list of EXACT order statistics (rank,
+        value), so the stored pair next below rank n - k + 1 bounds the k-th largest value from below; (2)
+        post_filter_agg_f64(field >= bound, terms_agg_u64(address column, max_agg_f64(field))) — the few documents at or
+        above the bound, keyed by their address, in the open-addressing bucket table."""
+        from .agg import ge, le, max_agg_f64, percentiles_agg_f64, post_filter_agg_f64, terms_agg_u64
+        if k <= 0:
+            return []
+        for i, seg in enumerate(self.segments):
+            if getattr(seg, "_doc_addr", None) != (self.DOC_ADDR_FIELD, i << 32):
+                seg.add_doc_address_column(self.DOC_ADDR_FIELD, i << 32)
+        p = self.agg_search(query, percentiles_agg_f64(field))
+        if p.n == 0:
+            return []
+        if descending:
+            bound = float("-inf")
+            for r, v in zip(p.ranks, p.values):
+                if r > p.n - k + 1:
+                    break
+                bound = v
+            pred = ge(bound)
+        else:
+            bound = float("inf")
+            for r, v in zip(reversed(p.ranks), reversed(p.values)):
+                if r < k:
+                    break
+                bound = v
+            pred = le(bound)
+        t = self.agg_search(query, post_filter_agg_f64(field, pred, terms_agg_u64(self.DOC_ADDR_FIELD, max_agg_f64(field))))
+        hits = sorted(((v, a >> 32, a & 0xFFFFFFFF) for a, v in t.res.items()), key=lambda h: (-h[0] if descending else h[0], h[1], h[2]))
+        return hits[:k]
 
     def agg_search_with_executor(self, query, agg, executor, collective=False, return_reader=False, root=None):
         """collective=True: every rank folds its own segments, one NCCL merge step, every rank returns the merged fruit;

@@ -129,3 +129,32 @@ def test_cardinality(dated):
     a = ta.Searcher(searcher.ctx, searcher.segments[:1]).agg_search(ta.AllQuery(), ta.cardinality_agg_u64s(TAGS_F))
     b = ta.Searcher(searcher.ctx, searcher.segments[1:]).agg_search(ta.AllQuery(), ta.cardinality_agg_u64s(TAGS_F))
     assert agg.merge(agg.merge(agg.create_fruit(), a), b).value == len(tags)
+
+
+@pytest.mark.parametrize("n", [30_000, 9_000_000])  # below / above the rank-bin threshold of the percentile pass
+def test_top_hits(ctx, n):
+    """README.md:42 top_hits: the k matched documents with the largest / smallest values of an f64 field, ties in document
+    order, against numpy — deletes and a bitset query in front, duplicates planted around the cut."""
+    rng = np.random.default_rng(n)
+    half = n // 3
+    vals = np.round(1.0 + 100.0 * rng.random(n), 3)
+    vals[rng.integers(0, n, size=50)] = 100.999  # ties at the top
+    vals[rng.integers(0, n, size=50)] = 1.0      # and at the bottom
+    segs = [SegSpec(half).col(PRICE, F.F64, vals[:half]), SegSpec(n - half).col(PRICE, F.F64, vals[half:])]
+    segs[0].deleted = range(0, half, 5)
+    searcher = Corpus(segs).build_gpu(ctx)
+    m = rng.random(n) < 0.7
+    q = ta.BitsetQuery({0: np.packbits(m[:half].astype(np.uint8), bitorder="little"), 1: np.packbits(m[half:].astype(np.uint8), bitorder="little")})
+    alive = m.copy()
+    alive[np.arange(0, half, 5)] = False
+    idx = np.nonzero(alive)[0]
+    seg_of = (idx >= half).astype(np.int64)
+    doc_of = np.where(idx >= half, idx - half, idx)
+    for k in (1, 10, 77):
+        for desc in (True, False):
+            order = np.lexsort((doc_of, seg_of, -vals[idx] if desc else vals[idx]))[:k]
+            want = [(float(vals[idx[o]]), int(seg_of[o]), int(doc_of[o])) for o in order]
+            assert searcher.top_hits_f64(q, PRICE, k, descending=desc) == want
+    assert searcher.top_hits_f64(q, PRICE, 0) == []
+    few = searcher.top_hits_f64(ta.DocIdsQuery({0: np.array([1, 2, 3], dtype=np.uint32), 1: np.array([], dtype=np.uint32)}), PRICE, 10)
+    assert [h[1:] for h in sorted(few, key=lambda h: h[2])] == [(0, 1), (0, 2), (0, 3)]
