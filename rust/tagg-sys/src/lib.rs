@@ -130,6 +130,8 @@ extern "C" {
     pub fn tagg_segment_max_doc(seg: *const tagg_segment, out: *mut u32) -> c_int;
     pub fn tagg_column_upload(seg: *mut tagg_segment, field_id: u32, kind: c_int, bytes: *const u8, len: usize) -> c_int;
     pub fn tagg_column_upload_codes(seg: *mut tagg_segment, field_id: u32, kind: c_int, codes: *const u64, n: usize) -> c_int;
+    /// u64 fast field `base + doc`, generated on the device: the key column of top_hits (include/tagg.h)
+    pub fn tagg_segment_doc_address_column(seg: *mut tagg_segment, field_id: u32, base: u64) -> c_int;
     pub fn tagg_multicolumn_upload(seg: *mut tagg_segment, field_id: u32, kind: c_int, idx_bytes: *const u8, idx_len: usize,
                                    vals_bytes: *const u8, vals_len: usize) -> c_int;
     pub fn tagg_multicolumn_upload_codes(seg: *mut tagg_segment, field_id: u32, kind: c_int, offsets: *const u64, n_offsets: usize,
