@@ -28,6 +28,9 @@
 // 5-document fixture (corpus: tests/golden/product_fixture.json; the tests themselves: tests/reference_cases.py, run on
 // the oracle by tests/test_oracle_golden.py); f64 min / max / sum around NaN, the signed zeros and the infinities are
 // pinned against a second, independent restatement of minmax.rs:97-106 / sum.rs:95-102 (tests/test_oracle_edge.py).
+// Beyond the reference: a HISTOGRAM node may key on an i64 / date column (date_histogram of the reference's TODO list,
+// README.md:31-45) — the same arithmetic on the timestamp as f64; pinned against numpy's integer floor division
+// (tests/test_oracle_extras.py).  No reference implementation exists for it.
 // PARITY UNPINNED at: the byte-level column layout (no reference test touches bytes — pinned
 // only against the spec-derived vectors of SURVEY.md Appendix A) and CKMS beyond n = 5
 // (compression never triggers in the reference test; the oracle CKMS is a tolerance witness).
