@@ -12,6 +12,9 @@ stream_fn stream_pick_ct_terms(uint32_t bops0, bool compact, bool stab, bool fil
         case OPB_MIN: return pick_ct_bucket<BK_TERMS, OPB_MIN>(compact, stab, filt);
         case OPB_MAX: return pick_ct_bucket<BK_TERMS, OPB_MAX>(compact, stab, filt);
         case OPB_SUM: return pick_ct_bucket<BK_TERMS, OPB_SUM>(compact, stab, filt);
+        case OPB_MIN | OPB_MAX: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX)>(compact, stab, filt);
+        case OPB_SUM | OPB_MIN: return pick_ct_bucket<BK_TERMS, (OPB_SUM | OPB_MIN)>(compact, stab, filt);
+        case OPB_SUM | OPB_MAX: return pick_ct_bucket<BK_TERMS, (OPB_SUM | OPB_MAX)>(compact, stab, filt);
         case OPB_MIN | OPB_MAX | OPB_SUM: return pick_ct_bucket<BK_TERMS, (OPB_MIN | OPB_MAX | OPB_SUM)>(compact, stab, filt);
     }
     return nullptr;
