@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
         uint32_t wtail = 0;
         TCol c_kc = {0, 0, 0, 0, 0, 0}, c_bc[NBG ? NBG : 1], c_rc[NRG ? NRG : 1];
         uint32_t c_seg = 0xffffffffu, c_base = 0, c_krel = 0;
+        uint32_t c_ptab = 0;  // cached truth tables of the bit-plane predicates (see the mask phase)
 #pragma unroll
         for (int g = 0; g < (NBG ? NBG : 1); g++) c_bc[g] = c_kc;
 #pragma unroll
@@ -432,10 +433,45 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                 if (flags & (SF_PRED_NONE0 * 15u)) m = 0;  // a filter query that matches nothing in this segment
             }
             // value predicates (post_filter / COLUMN_RANGE docsets): per document, folded in with ballots
+            const uint32_t tseg = lds32(T + TD_SEG);
             if (p.n_vpreds) {
+                // bit planes of a 1- or 2-bit column under a truth table `tt` over its values -> mask word of documents
+                // [32 lane, 32 lane + 32) for lanes < 8
+                auto planes = [&](uint32_t nb, uint32_t tt, uint32_t saddr) -> uint32_t {
+                    uint32_t pm = 0;
+                    if (lane < ST_WORDS_PER_WARP) {
+                        if (nb == 1) {
+                            const uint32_t x = lds32(saddr + (warp * ST_WORDS_PER_WARP + lane) * 4);
+                            pm = ((tt & 1u) ? ~x : 0u) | ((tt & 2u) ? x : 0u);
+                        } else {
+                            const uint64_t x = lds64(saddr + (warp * ST_WORDS_PER_WARP + lane) * 8);
+                            const uint32_t M0 = (tt & 1u) ? 0x55555555u : 0u, M1 = (tt & 2u) ? 0x55555555u : 0u;
+                            const uint32_t M2 = (tt & 4u) ? 0x55555555u : 0u, M3 = (tt & 8u) ? 0x55555555u : 0u;
+                            auto half = [&](uint32_t h) {
+                                const uint32_t b0 = h, b1 = h >> 1;  // (the table masks keep the even bit positions only)
+                                uint32_t r = (M0 & ~b1 & ~b0) | (M1 & ~b1 & b0) | (M2 & b1 & ~b0) | (M3 & b1 & b0);
+                                r = (r | (r >> 1)) & 0x33333333u;
+                                r = (r | (r >> 2)) & 0x0f0f0f0fu;
+                                r = (r | (r >> 4)) & 0x00ff00ffu;
+                                r = (r | (r >> 8)) & 0x0000ffffu;
+                                return r;
+                            };
+                            pm = half((uint32_t)x) | (half((uint32_t)(x >> 32)) << 16);
+                        }
+                    }
+                    return pm;
+                };
                 for (int i = 0; i < p.n_preds; i++) {
                     const int type = p.pred_type[i];
                     if (type == PR_FILTER) continue;
+                    // a truth table depends on the segment only (column min_value, predicate bounds): tiles of the same segment
+                    // reuse it — byte i of c_ptab = 0x80 | width << 4 | table
+                    const uint32_t pb = (c_ptab >> (8 * i)) & 0xffu;
+                    if (tseg == c_seg && (pb & 0x80u)) {
+                        m &= planes((pb >> 4) & 3u, pb & 15u, stage_saddr + p.soff_col[p.pred_scol[i]]);
+                        continue;
+                    }
+                    c_ptab &= ~(0xffu << (8 * i));
                     const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
                     const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
                     const uint8_t* lut = p.pred_lut[i];
@@ -455,29 +491,9 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                                 tv = code >= lo && code <= hi;
                             }
                         }
-                        const uint32_t T = __ballot_sync(0xffffffffu, tv);
-                        uint32_t pm = 0;
-                        if (lane < ST_WORDS_PER_WARP) {
-                            if (pc.nb == 1) {
-                                const uint32_t x = lds32(pc.saddr + (warp * ST_WORDS_PER_WARP + lane) * 4);
-                                pm = ((T & 1u) ? ~x : 0u) | ((T & 2u) ? x : 0u);
-                            } else {
-                                const uint64_t x = lds64(pc.saddr + (warp * ST_WORDS_PER_WARP + lane) * 8);
-                                const uint32_t M0 = (T & 1u) ? 0x55555555u : 0u, M1 = (T & 2u) ? 0x55555555u : 0u;
-                                const uint32_t M2 = (T & 4u) ? 0x55555555u : 0u, M3 = (T & 8u) ? 0x55555555u : 0u;
-                                auto half = [&](uint32_t h) {
-                                    const uint32_t b0 = h, b1 = h >> 1;  // (the table masks keep the even bit positions only)
-                                    uint32_t r = (M0 & ~b1 & ~b0) | (M1 & ~b1 & b0) | (M2 & b1 & ~b0) | (M3 & b1 & b0);
-                                    r = (r | (r >> 1)) & 0x33333333u;
-                                    r = (r | (r >> 2)) & 0x0f0f0f0fu;
-                                    r = (r | (r >> 4)) & 0x00ff00ffu;
-                                    r = (r | (r >> 8)) & 0x0000ffffu;
-                                    return r;
-                                };
-                                pm = half((uint32_t)x) | (half((uint32_t)(x >> 32)) << 16);
-                            }
-                        }
-                        m &= pm;
+                        const uint32_t tt = __ballot_sync(0xffffffffu, tv) & 15u;
+                        c_ptab |= (0x80u | (pc.nb << 4) | tt) << (8 * i);
+                        m &= planes(pc.nb, tt, pc.saddr);
                         continue;
                     }
                     if (pc.nb >= 1 && pc.nb <= 8 && (type == PR_RANGE || hi <= 32)) {
@@ -541,7 +557,6 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
             // (bit width, min_value), so a tile of the same segment just moves the shared-memory address
             TCol kc, bc[NBG ? NBG : 1], rc[NRG ? NRG : 1];
             uint32_t krel = 0;  // TERMS: (column min - domain min); keys are dense and < 2^24 wide
-            const uint32_t tseg = lds32(T + TD_SEG);
             if (tseg != c_seg) {
                 if (BUCKET != BK_NONE) {
                     kc = tcol(p, T, stage_saddr, p.key_scol);
