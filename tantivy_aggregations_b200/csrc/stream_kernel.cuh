@@ -466,12 +466,13 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                     if (type == PR_FILTER) continue;
                     // a truth table depends on the segment only (column min_value, predicate bounds): tiles of the same segment
                     // reuse it — byte i of c_ptab = 0x80 | width << 4 | table
+                    // (not in the rank-bin kernels: they are instruction-cache sensitive, +5 % with this path compiled in)
                     const uint32_t pb = (c_ptab >> (8 * i)) & 0xffu;
-                    if (tseg == c_seg && (pb & 0x80u)) {
+                    if (BUCKET != BK_RANK && tseg == c_seg && (pb & 0x80u)) {
                         m &= planes((pb >> 4) & 3u, pb & 15u, stage_saddr + p.soff_col[p.pred_scol[i]]);
                         continue;
                     }
-                    c_ptab &= ~(0xffu << (8 * i));
+                    if (BUCKET != BK_RANK) c_ptab &= ~(0xffu << (8 * i));
                     const TCol pc = tcol(p, T, stage_saddr, p.pred_scol[i]);
                     const uint64_t lo = lds64(T + TD_PRED_LO(i)), hi = lds64(T + TD_PRED_HI(i));
                     const uint8_t* lut = p.pred_lut[i];
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(ST_GROUP_THREADS * ST_MAXGROUPS) k_stream(cons
                             }
                         }
                         const uint32_t tt = __ballot_sync(0xffffffffu, tv) & 15u;
-                        c_ptab |= (0x80u | (pc.nb << 4) | tt) << (8 * i);
+                        if (BUCKET != BK_RANK) c_ptab |= (0x80u | (pc.nb << 4) | tt) << (8 * i);
                         m &= planes(pc.nb, tt, pc.saddr);
                         continue;
                     }
