@@ -66,6 +66,7 @@ def plans():
         "terms": lambda: ta.terms_agg_u64(1, (ta.count_agg(), ta.min_agg_f64(2), ta.sum_agg_f64(2))),
         "nested": lambda: ta.terms_agg_u64s(4, (ta.count_agg(), ta.histogram_agg_f64(2, 0.0, 20.0, (ta.count_agg(), ta.max_agg_f64(2))))),
         "post_filter": lambda: ta.post_filter_agg_i64(3, ta.ge(0), ta.terms_agg_i64(3, ta.count_agg())),
+        "date_histogram": lambda: ta.terms_agg_u64(1, ta.date_histogram_agg(3, 7, (ta.count_agg(), ta.sum_agg_f64(2)), start=-20, kind=ta.I64)),
     }
 
 
